@@ -1,0 +1,148 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run in the build container only (``python tests/golden/make_golden.py``): it imports
+``sif_functions`` / ``sif`` / ``losses`` / ``models`` from /root/reference, feeds them the
+seeded inputs built by ``tests/golden/cases.py`` and stores inputs that are small (or the
+seed that regenerates them, plus a checksum) together with the reference's outputs.
+/root/reference does not exist on the GPU box; tests only read the committed ``.npz``.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get('MMB_REFERENCE', '/root/reference')
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+sys.path.insert(1, HERE)
+
+import torch  # noqa: E402
+
+import sif_functions as ref_sf  # noqa: E402  (reference)
+import sif as ref_sif  # noqa: E402  (reference)
+import losses as ref_losses  # noqa: E402  (reference)
+import models as ref_models  # noqa: E402  (reference)
+
+import cases  # noqa: E402  (ours: seeded input builders shared with the tests)
+
+assert ref_sf.__file__.startswith(REF), ref_sf.__file__
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **arrs)
+    print('wrote', name, {k: getattr(v, 'shape', None) for k, v in arrs.items()},
+          os.path.getsize(path) // 1024, 'KiB')
+
+
+def sif_case(name, We, weights, ids, store_inputs):
+    w = ref_sf.seq2weight(ids, np.ones(ids.shape), weights)
+    avg = ref_sf.get_weighted_average(We, ids, w)
+    pc = ref_sf.compute_pc(avg, 1)
+    emb = ref_sif.get_sentence_embeddings(We, weights, ids)
+    keep = slice(0, 64)   # the fixtures stay small: first 64 rows + whole-array checksums
+    out = dict(w=w, avg=avg[keep], pc=pc, emb=emb[keep], avg_sum=cases.checksum(avg),
+               emb_sum=cases.checksum(emb), table_sum=cases.checksum(We))
+    if store_inputs:
+        out.update(We=We, weights=weights, ids=ids)
+    save(name, **out)
+
+
+def main():
+    # ---- SIF: MOSI-like small case, inputs stored (N < 300 -> sklearn transposes) -----
+    We, weights, ids = cases.sif_mosi_like()
+    sif_case('sif_mosi_like.npz', We, weights, ids, store_inputs=True)
+
+    # ---- SIF: N >= 300 rows, short rows, negative ids present ---------------------------
+    We, weights, ids = cases.sif_tall()
+    sif_case('sif_tall.npz', We, weights, ids, store_inputs=True)
+
+    # ---- SIF: real POM test ids (first 8 utterances, L=1357) + real POM word weights ----
+    pom_ids = np.load(os.path.join(REF, 'pom', 'pom_test_ids.npy'))
+    pom_w = np.load(os.path.join(REF, 'pom', 'pom_word_weights.npy')).squeeze()
+    ids = pom_ids[:8]
+    We = cases.table(7763, 300, seed=11)
+    w = ref_sf.seq2weight(ids, np.ones(ids.shape), pom_w)
+    avg = ref_sf.get_weighted_average(We, ids, w)
+    emb = ref_sif.get_sentence_embeddings(We, pom_w, ids)
+    save('sif_pom_real.npz', ids=ids.astype(np.int16), weights=pom_w, w_rowsum=w.sum(1),
+         w_nonzero=np.count_nonzero(w, axis=1), avg=avg, emb=emb, pc=ref_sf.compute_pc(avg, 1),
+         table_sum=cases.checksum(We),
+         valid_shape=np.array(np.load(os.path.join(REF, 'pom', 'pom_valid_ids.npy')).shape))
+
+    # ---- compute_pc / remove_pc on bare matrices, npc in {1,2,3}, both N regimes --------
+    out = {}
+    for tag, (n, gap, seed) in cases.PC_CASES.items():
+        X = cases.pc_matrix(n, gap, seed)
+        out[tag + '_sum'] = cases.checksum(X)
+        for npc in (1, 2, 3):
+            out['%s_pc%d' % (tag, npc)] = ref_sf.compute_pc(X, npc)
+            out['%s_rm%d' % (tag, npc)] = ref_sf.remove_pc(X, npc)[:16]
+    save('pc_cases.npz', **out)
+
+    # ---- MMB: losses + heads, values and autograd gradients -----------------------------
+    for tag, cfg in cases.MMB_CASES.items():
+        c = cases.mmb_inputs(**cfg)
+        torch.manual_seed(cfg['seed'])
+        model = ref_models.AudioVisualGeneratorMultimodal(
+            c['d'], c['A'], c['Vd'], norm=cfg['norm'], frozen_weights=False,
+            unimodal=cfg['unimodal'])
+        cases.load_heads(model, c['heads'], c.get('norm_params'))
+        lat = torch.tensor(c['latents'], requires_grad=True)
+        out_heads = model(lat)
+        t = {k: torch.tensor(v) for k, v in c.items() if isinstance(v, np.ndarray)}
+        text_gauss, text_gauss_m = t['text'], t['text_m']
+        if cfg['unimodal']:
+            data = {'text': t['text'], 'audio': t['aud'], 'visual': t['vis'],
+                    'text_weights': t['text_w']}
+            masks = {'text': t['text_m'], 'audio': t['aud_m'], 'visual': t['vis_m']}
+        else:  # simplesif.py:94-113
+            data = {'text': t['text'], 'audio': t['aud'], 'visual': t['vis'],
+                    'text_weights': t['text_w'],
+                    'audiovisual': torch.cat([t['aud'], t['vis']], -1),
+                    'textaudio': torch.cat([text_gauss, t['aud']], -1),
+                    'textvisual': torch.cat([text_gauss, t['vis']], -1),
+                    'textaudiovisual': torch.cat([text_gauss, t['aud'], t['vis']], -1)}
+            masks = {'text': t['text_m'], 'audio': t['aud_m'], 'visual': t['vis_m'],
+                     'audiovisual': torch.cat([t['aud_m'], t['vis_m']], -1),
+                     'textaudio': torch.cat([text_gauss_m, t['aud_m']], -1),
+                     'textvisual': torch.cat([text_gauss_m, t['vis_m']], -1),
+                     'textaudiovisual': torch.cat([text_gauss_m, t['aud_m'], t['vis_m']], -1)}
+        We_t = t['We']
+        a = 1e-3
+
+        def word_fn(latents, word_weights, sent_embeddings, mask):  # simplesif.py:527-537
+            return ref_losses.get_word_log_prob_angular2(latents, We_t, word_weights,
+                                                         sent_embeddings, mask, a)
+        args = dict(cfg['args'])
+        total = ref_losses.get_log_prob_matrix(args, lat, out_heads, data, masks, word_fn)
+        loss = (-total).mean()                                      # simplesif.py:129-134
+        loss.backward()
+        res = dict(total=total.detach().numpy(), loss=loss.detach().numpy(),
+                   grad_latents=lat.grad.numpy())
+        for mod, dd in out_heads.items():
+            res['mu_' + mod] = dd['mu'].detach().numpy()
+            res['sigma_' + mod] = dd['sigma'].detach().numpy()
+            res['lp_' + mod] = ref_losses.get_normal_log_prob(
+                dd['mu'].unsqueeze(1), dd['sigma'].unsqueeze(1), data[mod], masks[mod]).detach().numpy()
+            for nm in ('mu', 'log_sigma'):
+                gW = model.embed2out[mod][nm].weight.grad.numpy()
+                # large case: keep 8 rows of each weight gradient + a checksum of all of it
+                res['gW_%s_%s' % (nm, mod)] = gW if gW.size <= 4096 else gW[:8]
+                res['gWsum_%s_%s' % (nm, mod)] = cases.checksum(gW)
+                res['gb_%s_%s' % (nm, mod)] = model.embed2out[mod][nm].bias.grad.numpy()
+        if model.norm is not None:
+            res['g_norm_w'] = model.norm.weight.grad.numpy()
+            res['g_norm_b'] = model.norm.bias.grad.numpy()
+        res['word_lp'] = word_fn(lat, data['text_weights'], data['text'], masks['text']).detach().numpy()
+        lat2 = torch.tensor(c['latents'], requires_grad=True)
+        word_fn(lat2, data['text_weights'], data['text'], masks['text']).sum().backward()
+        res['word_grad'] = lat2.grad.numpy()
+        res['inputs_sum'] = cases.checksum(np.concatenate(
+            [c[k].ravel() for k in sorted(c) if isinstance(c[k], np.ndarray)]))
+        save('mmb_%s.npz' % tag, **res)
+
+
+if __name__ == '__main__':
+    main()
