@@ -1,0 +1,178 @@
+/*
+ * mmb_b200.h -- C ABI of libmmb_b200.so, the sm_100a implementation of the SIF / MMB
+ * utterance-embedding hot path of yaochie/multimodal-baselines.
+ *
+ * The reference has no FFI of its own (pure Python); the boundary is the module-level
+ * Python API of sif_functions.py / sif.py / losses.py / models.py / simplesif.py
+ * (SURVEY.md section 8b).  Every entry point below names the reference function
+ * (file:line under the reference tree) whose arithmetic it replaces.  The Python shims in
+ * multimodal-baselines_b200/ bind these with ctypes and keep the
+ * reference's names, argument order and error behaviour.
+ *
+ * Conventions
+ *   - plain C types only; all "device" pointers are CUDA device pointers owned by the
+ *     caller (torch allocates them); the library allocates nothing persistent except in
+ *     the *_host entry points, which own their staging buffers for the call's duration;
+ *   - every launch goes to the cudaStream_t passed as `stream` (0 = legacy default) and
+ *     returns without synchronising unless stated otherwise;
+ *   - return value 0 = success; non-zero = MMB_E_* below, message in mmb_last_error();
+ *   - matrices are row-major and dense unless a leading dimension is given;
+ *   - `status` words are device ints the kernels OR error bits into (MMB_STATUS_*); the
+ *     caller zeroes them, and reads them back when it next synchronises.
+ */
+#ifndef MMB_B200_H
+#define MMB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mmb_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define MMB_API __attribute__((visibility("default")))
+#else
+#define MMB_API
+#endif
+
+enum {
+  MMB_OK = 0,
+  MMB_E_INVALID = 1,     /* bad argument (null pointer, unsupported size)            */
+  MMB_E_CUDA = 2,        /* a CUDA runtime call failed; see mmb_last_error()         */
+  MMB_E_UNSUPPORTED = 3, /* valid request this build / device cannot run             */
+  MMB_E_INDEX = 4        /* token id outside [-V, V): the reference's IndexError      */
+};
+
+enum {
+  MMB_STATUS_BAD_INDEX = 1, /* an id was outside [-V, V) (NumPy would raise IndexError) */
+  MMB_STATUS_NONFINITE = 2  /* a log-probability was +-inf/NaN (losses.py:258-264)      */
+};
+
+enum { /* mmb_gram `mode` */
+  MMB_GRAM_AUTO = 0,
+  MMB_GRAM_FP32 = 1,     /* CUDA-core FP32 FMA, split-K, deterministic 2-stage reduce  */
+  MMB_GRAM_TF32X3 = 2    /* tcgen05 kind::tf32, 3xTF32 split (hi*hi + hi*lo + lo*hi)   */
+};
+
+/* ---------------------------------------------------------------- library --------- */
+MMB_API int mmb_version(void);
+MMB_API const char* mmb_last_error(void);
+/* sm_count / cc_major / cc_minor of the current device (any pointer may be NULL). */
+MMB_API int mmb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Pinned host memory for the *_host entry points and for e2e benchmarks. */
+MMB_API int mmb_host_alloc(void** ptr, size_t bytes);
+MMB_API int mmb_host_free(void* ptr);
+
+/* ---------------------------------------------------------------- SIF (A1-A5) ----- */
+
+/* seq2weight -- sif_functions.py:8-15.
+ * w[i,j] = weight4ind[seq[i,j]] if (mask == NULL || mask[i,j] > 0) && seq[i,j] >= 0, else 0.
+ * weight4ind is the float32 image of the reference's float64 vector (the reference casts
+ * on assignment into its float32 array, line 9/13).  ids >= V set MMB_STATUS_BAD_INDEX. */
+MMB_API int mmb_seq2weight(const int64_t* seq, const float* mask, const float* weight4ind, int64_t V,
+                   int64_t N, int64_t L, float* w, int* status, mmb_stream_t stream);
+
+/* get_weighted_average -- sif_functions.py:28-56 with explicit per-token weights.
+ * emb[i,:] = (sum_j w[i,j] * table[x[i,j],:]) / count_nonzero(w[i,:]); negative ids index
+ * from the end of the table as NumPy does; FP32 accumulate in token order.            */
+MMB_API int mmb_weighted_average(const float* table, int64_t V, int d, const int64_t* x, const float* w,
+                         int64_t N, int64_t L, float* emb, int* status, mmb_stream_t stream);
+
+/* seq2weight (mask of ones, sif.py:78-82) fused into get_weighted_average: the (N,L)
+ * weight matrix never exists.  w[i,j] = vocab_w[x[i,j]] if x[i,j] >= 0 else 0.         */
+MMB_API int mmb_sif_embed(const float* table, int64_t V, int d, const float* vocab_w, const int64_t* x,
+                  int64_t N, int64_t L, float* emb, int* status, mmb_stream_t stream);
+
+/* compute_pc part 1 -- sif_functions.py:58-67: G = X^T X (d x d, float32), no centring.
+ * `ws` is scratch of at least mmb_gram_workspace_bytes(N, d, mode) bytes.             */
+MMB_API size_t mmb_gram_workspace_bytes(int64_t N, int d, int mode);
+MMB_API int mmb_gram(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_bytes, int mode,
+             mmb_stream_t stream);
+
+/* compute_pc part 2: the components sklearn's TruncatedSVD(npc, n_iter=7, random_state=0)
+ * returns, as a function of G and the seeded start block S0 (d x k, row-major float64,
+ * k = npc + 10): S0 = RandomState(0).normal(size=(d,k)) when N >= d (transposed = 0), or
+ * X^T RandomState(0).normal(size=(N,k)) when N < d (transposed = 1); see
+ * oracle/sif_oracle.py:compute_pc_from_gram.  pc is (npc, d) float32, unit rows, largest
+ * |entry| of each row positive (sklearn svd_flip, u_based_decision=False).  One CTA, FP64.
+ * `ws` is scratch of at least mmb_pc_workspace_bytes(d, k) bytes.                      */
+MMB_API size_t mmb_pc_workspace_bytes(int d, int k);
+MMB_API int mmb_pc_from_gram(const float* G, int d, const double* S0, int k, int npc, int transposed,
+                     int n_iter, float* pc, void* ws, size_t ws_bytes, mmb_stream_t stream);
+/* S0 for the N < d case: S0 = X^T Omega (Omega is N x k float64, row-major).            */
+MMB_API int mmb_start_block_xt(const float* X, int64_t N, int d, const double* Omega, int k, double* S0,
+                       mmb_stream_t stream);
+
+/* remove_pc -- sif_functions.py:69-81 given the components:
+ * out = X - (X pc^T) pc  (npc == 1: line 78; npc > 1: line 80).  out may alias X.      */
+MMB_API int mmb_remove_pc(const float* X, int64_t N, int d, const float* pc, int npc, float* out,
+                  mmb_stream_t stream);
+
+/* get_sentence_embeddings -- sif.py:84-94 on ONE device, everything resident in HBM:
+ * embed -> Gram -> components (npc, 0 = skip PC removal) -> projection, no host sync.
+ * `Omega` is the seeded start block for this (N, npc) (d x k if N >= d else N x k).
+ * `ws` >= mmb_sif_workspace_bytes(N, d, npc).  emb is (N, d) float32; pc (npc, d) and
+ * G (d, d) are written when non-NULL outputs are given.                                */
+MMB_API size_t mmb_sif_workspace_bytes(int64_t N, int d, int npc);
+MMB_API int mmb_sif_embedding(const float* table, int64_t V, int d, const float* vocab_w,
+                      const int64_t* x, int64_t N, int64_t L, int npc, const double* Omega,
+                      float* emb, float* pc, float* G, void* ws, size_t ws_bytes, int gram_mode,
+                      int* status, mmb_stream_t stream);
+
+/* The same call with HOST buffers (ids, Omega in; emb out), as the reference's NumPy
+ * caller sees it: H2D of the ids in chunks overlapped with the embed kernel, one Gram +
+ * solve, projection overlapped with the D2H of the result.  `table_dev` / `vocab_w_dev`
+ * stay on the device (upload once with cudaMemcpy / torch).  x_host and emb_host should be
+ * pinned (mmb_host_alloc) for full PCIe rate.  emb_f64 != 0 writes float64 like the
+ * reference's np.zeros((N,d)) (sif_functions.py:37), else float32.  Synchronous.       */
+MMB_API int mmb_sif_embedding_host(const float* table_dev, int64_t V, int d, const float* vocab_w_dev,
+                           const int64_t* x_host, int64_t N, int64_t L, int npc,
+                           const double* Omega_host, void* emb_host, int emb_f64,
+                           float* pc_host, int gram_mode, int64_t chunk_rows);
+
+/* ---------------------------------------------------------------- MMB (A6-A9) ----- */
+
+/* AudioVisualGeneratorMultimodal.forward -- models.py:187-202, all heads in one launch.
+ * z (B, d) is the (already normalised) latent batch.  Head h (h < n_heads) has weight
+ * W[h] (D[h], d) and bias b[h] (D[h]); heads come in (mu, log_sigma) pairs per modality
+ * and `is_log_sigma[h]` selects the exp() epilogue.  out[h] is (B, D[h]).
+ * Pointer tables are DEVICE arrays of device pointers.                                 */
+MMB_API int mmb_heads_forward(const float* z, int B, int d, int n_heads, const float* const* W,
+                      const float* const* b, const int* D, const int* is_log_sigma,
+                      float* const* out, int max_D, mmb_stream_t stream);
+
+/* get_normal_log_prob -- losses.py:13-34, for every modality of MMB1/MMB2 at once,
+ * forward and the analytic gradients, reading each base tensor
+ * (text_gauss, audio, visual) and its 0/1 float mask exactly once instead of the
+ * concatenations of simplesif.py:94-113.
+ *   base[s]  (B, T, F[s]) values, bmask[s] same shape, s in {0:text, 1:audio, 2:visual};
+ *   modality m is the concatenation of the bases whose bit is set in mod_bases[m]
+ *   (bit s = base s), in base order, like the reference's torch.cat;
+ *   mu[m], log_sigma[m]: (B, Dm) with Dm = sum of its bases' F;
+ *   lp (n_mod, B) log-likelihoods; dmu[m], dls[m] (B, Dm) = d lp[m] / d mu, d log_sigma.
+ * `status` gets MMB_STATUS_NONFINITE if any lp is not finite (losses.py:258-264).      */
+MMB_API int mmb_gauss_ll(const float* const* base, const float* const* bmask, const int* F, int B, int T,
+                 int n_mod, const int* mod_bases, const float* const* mu,
+                 const float* const* log_sigma, float* lp, float* const* dmu, float* const* dls,
+                 int* status, mmb_stream_t stream);
+
+/* get_word_log_prob_angular2 -- losses.py:68-95 forward + d/d latents (Appendix A.5).
+ *   latents (B, d); table (V, d) and its per-row inverse norms inv_norm (V) (constant
+ *   across steps: mmb_row_inv_norm); sent (B, L, d) token vectors, word_w (B, L),
+ *   tmask (B, L) = mask[:, :, 0]; a = 1e-3 (simplesif.py:513).
+ *   lp (B) and grad (B, d) = d lp / d latents.  ws >= mmb_word_ll_workspace_bytes(B, V). */
+MMB_API int mmb_row_inv_norm(const float* table, int64_t V, int d, float* inv_norm, mmb_stream_t stream);
+MMB_API size_t mmb_word_ll_workspace_bytes(int B, int64_t V, int L);
+MMB_API int mmb_word_ll(const float* latents, int B, int d, const float* table, const float* inv_norm,
+                int64_t V, const float* sent, int64_t sent_stride_b, int64_t sent_stride_t,
+                const float* word_w, const float* tmask, int64_t tmask_stride_b,
+                int64_t tmask_stride_t, int L, float a, float* lp, float* grad, void* ws,
+                size_t ws_bytes, int* status, mmb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMB_B200_H */

@@ -1,0 +1,346 @@
+// libmmb_b200.so: library plumbing (errors, device info, pinned memory), the Gram dispatcher
+// and the composed SIF pipelines (device-resident and host-buffer variants).
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace mmb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return MMB_E_CUDA;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cached;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+      cached = n;
+      cached_dev = dev;
+    }
+  }
+  return cached;
+}
+
+// implemented in gram_fp32.cu / gram_tc.cu
+size_t gram_fp32_workspace_bytes(int64_t N, int d);
+int gram_fp32(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t gram_tc_workspace_bytes(int64_t N, int d);
+int gram_tc(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_bytes, cudaStream_t st);
+bool gram_tc_supported(int64_t N, int d);
+
+static int resolve_gram_mode(int64_t N, int d, int mode) {
+  if (mode == MMB_GRAM_AUTO) return gram_tc_supported(N, d) ? MMB_GRAM_TF32X3 : MMB_GRAM_FP32;
+  return mode;
+}
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+__global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restrict__ out, int64_t n) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (double)__ldcs(in + i);
+}
+
+}  // namespace mmb
+
+using namespace mmb;
+
+extern "C" int mmb_version(void) { return 100; }
+
+extern "C" const char* mmb_last_error(void) { return g_err; }
+
+extern "C" int mmb_device_info(int* sm, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  MMB_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  MMB_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm) *sm = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return MMB_OK;
+}
+
+extern "C" int mmb_host_alloc(void** ptr, size_t bytes) {
+  MMB_REQUIRE(ptr, "null pointer");
+  MMB_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return MMB_OK;
+}
+
+extern "C" int mmb_host_free(void* ptr) {
+  if (ptr) MMB_CUDA(cudaFreeHost(ptr));
+  return MMB_OK;
+}
+
+extern "C" size_t mmb_gram_workspace_bytes(int64_t N, int d, int mode) {
+  size_t a = gram_fp32_workspace_bytes(N, d);
+  if (mode != MMB_GRAM_FP32 && gram_tc_supported(N, d)) {
+    size_t b = gram_tc_workspace_bytes(N, d);
+    if (b > a) a = b;
+  }
+  return a;
+}
+
+extern "C" int mmb_gram(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_bytes, int mode,
+                        mmb_stream_t stream) {
+  MMB_REQUIRE(X && G && ws, "null pointer");
+  MMB_REQUIRE(d > 0 && d % 4 == 0, "d must be a positive multiple of 4");
+  MMB_REQUIRE(N >= 0, "negative N");
+  MMB_REQUIRE((uintptr_t)X % 16 == 0, "X must be 16-byte aligned");
+  mode = resolve_gram_mode(N, d, mode);
+  if (mode == MMB_GRAM_FP32) return gram_fp32(X, N, d, G, ws, ws_bytes, as_stream(stream));
+  if (mode == MMB_GRAM_TF32X3) {
+    if (!gram_tc_supported(N, d)) {
+      set_error("mmb_gram: the tcgen05 path needs d == 300 and N >= 1 on an sm_100 device");
+      return MMB_E_UNSUPPORTED;
+    }
+    return gram_tc(X, N, d, G, ws, ws_bytes, as_stream(stream));
+  }
+  set_error("mmb_gram: unknown mode %d", mode);
+  return MMB_E_INVALID;
+}
+
+// ---- composed pipeline, everything resident on the device ---------------------------------
+struct SifWs {
+  size_t gram, pc, s0, G, pcv, total;
+};
+static SifWs sif_ws_layout(int64_t N, int d, int npc) {
+  SifWs w;
+  const int k = npc + 10;
+  size_t off = 0;
+  w.gram = off; off += align_up(mmb_gram_workspace_bytes(N, d, MMB_GRAM_AUTO));
+  w.pc = off;   off += align_up(mmb_pc_workspace_bytes(d, k));
+  w.s0 = off;   off += align_up((size_t)d * k * sizeof(double));
+  w.G = off;    off += align_up((size_t)d * d * sizeof(float));
+  w.pcv = off;  off += align_up((size_t)(npc > 0 ? npc : 1) * d * sizeof(float));
+  w.total = off;
+  return w;
+}
+
+extern "C" size_t mmb_sif_workspace_bytes(int64_t N, int d, int npc) {
+  return sif_ws_layout(N, d, npc > 0 ? npc : 1).total;
+}
+
+// Gram -> components -> projection on an (N, d) embedding block already on the device.
+static int pc_removal_device(float* emb, int64_t N, int d, int npc, const double* Omega, float* pc_out,
+                             float* G_out, void* ws, size_t ws_bytes, int gram_mode, cudaStream_t st) {
+  const int k = npc + 10;
+  MMB_REQUIRE(k <= 32, "npc must be <= 22");
+  SifWs L = sif_ws_layout(N, d, npc);
+  MMB_REQUIRE(ws && ws_bytes >= L.total, "workspace too small");
+  MMB_REQUIRE(Omega, "Omega (seeded start block) is required when npc > 0");
+  char* base = (char*)ws;
+  float* G = G_out ? G_out : (float*)(base + L.G);
+  float* pc = pc_out ? pc_out : (float*)(base + L.pcv);
+  int rc = mmb_gram(emb, N, d, G, base + L.gram, L.pc - L.gram, gram_mode, st);
+  if (rc) return rc;
+  const double* S0 = Omega;
+  const int transposed = N < d;
+  if (transposed) {
+    rc = mmb_start_block_xt(emb, N, d, Omega, k, (double*)(base + L.s0), st);
+    if (rc) return rc;
+    S0 = (const double*)(base + L.s0);
+  }
+  rc = mmb_pc_from_gram(G, d, S0, k, npc, transposed, 7, pc, base + L.pc, L.s0 - L.pc, st);
+  if (rc) return rc;
+  return mmb_remove_pc(emb, N, d, pc, npc, emb, st);
+}
+
+extern "C" int mmb_sif_embedding(const float* table, int64_t V, int d, const float* vocab_w,
+                                 const int64_t* x, int64_t N, int64_t L, int npc, const double* Omega,
+                                 float* emb, float* pc, float* G, void* ws, size_t ws_bytes,
+                                 int gram_mode, int* status, mmb_stream_t stream) {
+  int rc = mmb_sif_embed(table, V, d, vocab_w, x, N, L, emb, status, stream);
+  if (rc || npc <= 0 || N == 0) return rc;
+  return pc_removal_device(emb, N, d, npc, Omega, pc, G, ws, ws_bytes, gram_mode, as_stream(stream));
+}
+
+// ---- the same call with host buffers --------------------------------------------------------
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  cudaStream_t st = nullptr;
+  int alloc(size_t bytes, cudaStream_t s) {
+    st = s;
+    MMB_CUDA(cudaMallocAsync(&p, bytes ? bytes : 16, s));
+    return MMB_OK;
+  }
+  ~DevBuf() {
+    if (p) cudaFreeAsync(p, st);
+  }
+};
+struct Streams {
+  cudaStream_t in = nullptr, comp = nullptr, out = nullptr;
+  std::vector<cudaEvent_t> ev;
+  int init() {
+    MMB_CUDA(cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking));
+    MMB_CUDA(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
+    MMB_CUDA(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
+    return MMB_OK;
+  }
+  int event(cudaEvent_t* e) {
+    MMB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    ev.push_back(*e);
+    return MMB_OK;
+  }
+  ~Streams() {
+    for (auto e : ev) cudaEventDestroy(e);
+    if (in) cudaStreamDestroy(in);
+    if (comp) cudaStreamDestroy(comp);
+    if (out) cudaStreamDestroy(out);
+  }
+};
+}  // namespace
+
+extern "C" int mmb_sif_embedding_host(const float* table_dev, int64_t V, int d, const float* vocab_w_dev,
+                                      const int64_t* x_host, int64_t N, int64_t L, int npc,
+                                      const double* Omega_host, void* emb_host, int emb_f64,
+                                      float* pc_host, int gram_mode, int64_t chunk_rows) {
+  MMB_REQUIRE(table_dev && vocab_w_dev && x_host && emb_host, "null pointer");
+  MMB_REQUIRE(N >= 0 && L >= 0 && d > 0 && d % 4 == 0, "bad size");
+  MMB_REQUIRE(npc >= 0 && npc + 10 <= 32, "npc must be in [0, 22]");
+  MMB_REQUIRE(npc == 0 || Omega_host, "Omega is required when npc > 0");
+  if (N == 0) return MMB_OK;
+  if (chunk_rows <= 0) chunk_rows = 1 << 18;
+  if (chunk_rows > N) chunk_rows = N;
+  const int64_t nchunks = ceil_div(N, chunk_rows);
+  const int k = npc + 10;
+
+  {  // keep freed blocks in the pool so repeated calls do not pay cudaMalloc again
+    int dev = 0;
+    MMB_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    MMB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = UINT64_MAX;
+    MMB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  Streams S;
+  int rc = S.init();
+  if (rc) return rc;
+  DevBuf ids[2], emb, ws, omega, status, pcv, f64[2];
+  const size_t ids_chunk = (size_t)chunk_rows * L * sizeof(int64_t);
+  if ((rc = ids[0].alloc(ids_chunk, S.comp))) return rc;
+  if ((rc = ids[1].alloc(ids_chunk, S.comp))) return rc;
+  if ((rc = emb.alloc((size_t)N * d * sizeof(float), S.comp))) return rc;
+  if ((rc = status.alloc(sizeof(int), S.comp))) return rc;
+  MMB_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), S.comp));
+  const size_t ws_bytes = mmb_sif_workspace_bytes(N, d, npc);
+  if (npc > 0) {
+    const int64_t orows = N >= d ? d : N;
+    if ((rc = ws.alloc(ws_bytes, S.comp))) return rc;
+    if ((rc = omega.alloc((size_t)orows * k * sizeof(double), S.comp))) return rc;
+    if ((rc = pcv.alloc((size_t)npc * d * sizeof(float), S.comp))) return rc;
+    MMB_CUDA(cudaMemcpyAsync(omega.p, Omega_host, (size_t)orows * k * sizeof(double),
+                             cudaMemcpyHostToDevice, S.comp));
+  }
+  if (emb_f64) {
+    const size_t b = (size_t)chunk_rows * d * sizeof(double);
+    if ((rc = f64[0].alloc(b, S.comp))) return rc;
+    if ((rc = f64[1].alloc(b, S.comp))) return rc;
+  }
+  cudaEvent_t allocs_done;
+  if ((rc = S.event(&allocs_done))) return rc;
+  MMB_CUDA(cudaEventRecord(allocs_done, S.comp));
+  MMB_CUDA(cudaStreamWaitEvent(S.in, allocs_done, 0));
+  MMB_CUDA(cudaStreamWaitEvent(S.out, allocs_done, 0));
+
+  // phase 1: ids H2D (stream `in`) overlapped with the embed kernel (stream `comp`)
+  cudaEvent_t in_ready[2], buf_free[2];
+  for (int b = 0; b < 2; ++b) {
+    if ((rc = S.event(&in_ready[b]))) return rc;
+    if ((rc = S.event(&buf_free[b]))) return rc;
+  }
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int b = (int)(c & 1);
+    const int64_t r0 = c * chunk_rows;
+    const int64_t rows = (N - r0) < chunk_rows ? (N - r0) : chunk_rows;
+    if (c >= 2) MMB_CUDA(cudaStreamWaitEvent(S.in, buf_free[b], 0));
+    MMB_CUDA(cudaMemcpyAsync(ids[b].p, x_host + r0 * L, (size_t)rows * L * sizeof(int64_t),
+                             cudaMemcpyHostToDevice, S.in));
+    MMB_CUDA(cudaEventRecord(in_ready[b], S.in));
+    MMB_CUDA(cudaStreamWaitEvent(S.comp, in_ready[b], 0));
+    rc = mmb_sif_embed(table_dev, V, d, vocab_w_dev, (const int64_t*)ids[b].p, rows, L,
+                       (float*)emb.p + r0 * d, (int*)status.p, S.comp);
+    if (rc) return rc;
+    MMB_CUDA(cudaEventRecord(buf_free[b], S.comp));
+  }
+  // phase 2: Gram + components on the whole block, then projection chunk by chunk
+  float* pc_dev = (float*)pcv.p;
+  if (npc > 0) {
+    SifWs Lw = sif_ws_layout(N, d, npc);
+    char* base = (char*)ws.p;
+    float* G = (float*)(base + Lw.G);
+    rc = mmb_gram((const float*)emb.p, N, d, G, base + Lw.gram, Lw.pc - Lw.gram, gram_mode, S.comp);
+    if (rc) return rc;
+    const double* S0 = (const double*)omega.p;
+    const int transposed = N < d;
+    if (transposed) {
+      rc = mmb_start_block_xt((const float*)emb.p, N, d, (const double*)omega.p, k,
+                              (double*)(base + Lw.s0), S.comp);
+      if (rc) return rc;
+      S0 = (const double*)(base + Lw.s0);
+    }
+    rc = mmb_pc_from_gram(G, d, S0, k, npc, transposed, 7, pc_dev, base + Lw.pc, Lw.s0 - Lw.pc, S.comp);
+    if (rc) return rc;
+  }
+  // phase 3: projection (stream `comp`) overlapped with the D2H of finished chunks (`out`)
+  cudaEvent_t out_ready[2], out_free[2];
+  for (int b = 0; b < 2; ++b) {
+    if ((rc = S.event(&out_ready[b]))) return rc;
+    if ((rc = S.event(&out_free[b]))) return rc;
+  }
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int b = (int)(c & 1);
+    const int64_t r0 = c * chunk_rows;
+    const int64_t rows = (N - r0) < chunk_rows ? (N - r0) : chunk_rows;
+    float* blk = (float*)emb.p + r0 * d;
+    if (npc > 0) {
+      rc = mmb_remove_pc(blk, rows, d, pc_dev, npc, blk, S.comp);
+      if (rc) return rc;
+    }
+    if (emb_f64) {
+      if (c >= 2) MMB_CUDA(cudaStreamWaitEvent(S.comp, out_free[b], 0));
+      const int64_t n = rows * d;
+      f32_to_f64_kernel<<<(int)(ceil_div(n, 1024) < 4096 ? ceil_div(n, 1024) : 4096), 256, 0, S.comp>>>(
+          blk, (double*)f64[b].p, n);
+      MMB_LAUNCH_CHECK("f32_to_f64");
+    }
+    MMB_CUDA(cudaEventRecord(out_ready[b], S.comp));
+    MMB_CUDA(cudaStreamWaitEvent(S.out, out_ready[b], 0));
+    if (emb_f64) {
+      MMB_CUDA(cudaMemcpyAsync((double*)emb_host + r0 * d, f64[b].p, (size_t)rows * d * sizeof(double),
+                               cudaMemcpyDeviceToHost, S.out));
+      MMB_CUDA(cudaEventRecord(out_free[b], S.out));
+    } else {
+      MMB_CUDA(cudaMemcpyAsync((float*)emb_host + r0 * d, blk, (size_t)rows * d * sizeof(float),
+                               cudaMemcpyDeviceToHost, S.out));
+    }
+  }
+  int h_status = 0;
+  if (pc_host && npc > 0)
+    MMB_CUDA(cudaMemcpyAsync(pc_host, pc_dev, (size_t)npc * d * sizeof(float), cudaMemcpyDeviceToHost, S.comp));
+  MMB_CUDA(cudaMemcpyAsync(&h_status, status.p, sizeof(int), cudaMemcpyDeviceToHost, S.comp));
+  MMB_CUDA(cudaStreamSynchronize(S.comp));
+  MMB_CUDA(cudaStreamSynchronize(S.out));
+  MMB_CUDA(cudaStreamSynchronize(S.in));
+  if (h_status & MMB_STATUS_BAD_INDEX) {
+    set_error("index out of bounds: a token id is outside [-%lld, %lld)", (long long)V, (long long)V);
+    return MMB_E_INDEX;
+  }
+  return MMB_OK;
+}

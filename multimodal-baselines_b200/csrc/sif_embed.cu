@@ -1,0 +1,279 @@
+// SIF weighted average (reference: sif_functions.py:8-15 seq2weight, 28-56
+// get_weighted_average; sif.py:78-94 glue).
+//
+// HBM/L2-bound gather + segmented weighted reduction.  One warp owns one utterance: the
+// 32 lanes first load 32 token ids (coalesced int64) and look up their weights, then the
+// warp walks the tokens in order; for each token the d-float table row is read as
+// coalesced float4 (d = 300 -> 75 float4 -> lanes 0..31, 0..31, 0..10) and FMA'd into
+// per-lane FP32 accumulators.  The (N, L) weight matrix of the reference never exists in
+// the fused path.  Summation is in token order, so the result is deterministic.
+//
+// Semantics kept from the reference:
+//   * divisor = count_nonzero(w[i, :]) over the whole padded row (pad id 0 counts when its
+//     weight is non-zero, as in the POM fixture);
+//   * id 0 is an ordinary row of the table;
+//   * negative ids: seq2weight gives them weight 0 (line 12) while NumPy's We[x] indexes
+//     from the end of the table, so the row is still read and multiplied by 0 (NaN/inf
+//     rows propagate exactly as in NumPy);
+//   * ids outside [-V, V) are NumPy's IndexError: the kernel skips them and raises
+//     MMB_STATUS_BAD_INDEX, which the Python shim turns into IndexError;
+//   * an all-zero-weight row divides by zero -> NaN row.
+#include "common.cuh"
+
+namespace mmb {
+
+constexpr int kEmbedWarps = 8;  // warps per CTA
+
+// A1: the stand-alone lookup (the reference materialises this matrix; the fused kernel
+// below does not).
+__global__ void __launch_bounds__(256) seq2weight_kernel(const int64_t* __restrict__ seq,
+                                                         const float* __restrict__ mask,
+                                                         const float* __restrict__ w4i, int64_t V,
+                                                         int64_t n, float* __restrict__ w,
+                                                         int* __restrict__ status) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t id = __ldcs(seq + i);
+    float m = mask ? __ldcs(mask + i) : 1.f;
+    float out = 0.f;
+    if (m > 0.f && id >= 0) {
+      if (id < V) out = __ldg(w4i + id);
+      else bad = true;
+    }
+    __stcs(w + i, out);
+  }
+  if (bad) atomicOr(status, MMB_STATUS_BAD_INDEX);
+}
+
+// One token's contribution: acc[c] += wj * row[lane + 32 c].
+template <int NCH>
+__device__ __forceinline__ void load_row(float4 (&v)[NCH], const float4* __restrict__ p, int lane,
+                                         int d4) {
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    int k = lane + 32 * c;
+    v[c] = ((NCH <= 4 && c + 1 < NCH) || k < d4) ? __ldg(p + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <int NCH>
+__device__ __forceinline__ void fma_row(float4 (&acc)[NCH], const float4 (&v)[NCH], float w) {
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    acc[c].x = fmaf(w, v[c].x, acc[c].x);
+    acc[c].y = fmaf(w, v[c].y, acc[c].y);
+    acc[c].z = fmaf(w, v[c].z, acc[c].z);
+    acc[c].w = fmaf(w, v[c].w, acc[c].w);
+  }
+}
+
+// Accumulate tokens [base, base+32) of utterance i (lane = token) into acc; returns the
+// number of non-zero weights among them.
+template <int NCH, bool EXPLICIT_W>
+__device__ __forceinline__ int accumulate_chunk(float4 (&acc)[NCH], const float4* __restrict__ table4,
+                                                int V, int d4, const float* __restrict__ wsrc,
+                                                const int64_t* __restrict__ row_ids,
+                                                const float* __restrict__ row_w, int64_t base,
+                                                int64_t L, int lane, bool& bad) {
+  const int64_t t = base + lane;
+  float w = 0.f;
+  int row = 0;
+  if (t < L) {
+    const int64_t id = __ldcs(row_ids + t);
+    const int64_t r = id < 0 ? id + V : id;
+    if (r >= 0 && r < V) {
+      row = (int)r;
+      w = EXPLICIT_W ? __ldcs(row_w + t) : (id >= 0 ? __ldg(wsrc + id) : 0.f);
+    } else {
+      bad = true;  // NumPy: IndexError
+    }
+  }
+  const int cnt = __popc(__ballot_sync(0xffffffffu, w != 0.f));
+  const int n_tok = (int)((L - base) < 32 ? (L - base) : 32);
+  int j = 0;
+  // 4 tokens per trip: 4 x NCH independent 16-byte loads in flight per lane before the FMAs.
+  for (; j + 4 <= n_tok; j += 4) {
+    float wj[4];
+    float4 v[4][NCH];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      wj[u] = __shfl_sync(0xffffffffu, w, j + u);
+      const int rj = __shfl_sync(0xffffffffu, row, j + u);
+      load_row<NCH>(v[u], table4 + (size_t)rj * d4, lane, d4);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) fma_row<NCH>(acc, v[u], wj[u]);
+  }
+  for (; j < n_tok; ++j) {
+    const float wj = __shfl_sync(0xffffffffu, w, j);
+    const int rj = __shfl_sync(0xffffffffu, row, j);
+    float4 v[NCH];
+    load_row<NCH>(v, table4 + (size_t)rj * d4, lane, d4);
+    fma_row<NCH>(acc, v, wj);
+  }
+  return cnt;
+}
+
+template <int NCH>
+__device__ __forceinline__ void store_row(float4* __restrict__ out, const float4 (&acc)[NCH],
+                                          int cnt, int lane, int d4) {
+  const float div = (float)cnt;  // 0 -> inf/NaN row, as NumPy's true_divide
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    int k = lane + 32 * c;
+    if ((NCH <= 4 && c + 1 < NCH) || k < d4) {
+      float4 r = acc[c];
+      r.x = __fdiv_rn(r.x, div);
+      r.y = __fdiv_rn(r.y, div);
+      r.z = __fdiv_rn(r.z, div);
+      r.w = __fdiv_rn(r.w, div);
+      st_stream(out + k, r);
+    }
+  }
+}
+
+// Warp-per-utterance variant (large N).
+template <int NCH, bool EXPLICIT_W>
+__global__ void __launch_bounds__(kEmbedWarps * 32)
+    sif_embed_warp_kernel(const float4* __restrict__ table4, int V, int d4,
+                          const float* __restrict__ wsrc, const int64_t* __restrict__ ids,
+                          int64_t N, int64_t L, float4* __restrict__ emb4,
+                          int* __restrict__ status) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kEmbedWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kEmbedWarps;
+  bool bad = false;
+  for (int64_t i = warp0; i < N; i += nwarps) {
+    float4 acc[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cnt = 0;
+    const int64_t* row_ids = ids + i * L;
+    const float* row_w = EXPLICIT_W ? wsrc + i * L : nullptr;
+    for (int64_t base = 0; base < L; base += 32)
+      cnt += accumulate_chunk<NCH, EXPLICIT_W>(acc, table4, V, d4, wsrc, row_ids, row_w, base, L,
+                                               lane, bad);
+    store_row<NCH>(emb4 + (size_t)i * d4, acc, cnt, lane, d4);
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, MMB_STATUS_BAD_INDEX);
+}
+
+// CTA-per-utterance variant (few, long utterances -- the POM shape: 203 x 1357): the 8
+// warps take 32-token chunks round-robin and are summed through shared memory in warp
+// order, so the result is still deterministic.
+template <int NCH, bool EXPLICIT_W>
+__global__ void __launch_bounds__(kEmbedWarps * 32)
+    sif_embed_cta_kernel(const float4* __restrict__ table4, int V, int d4,
+                         const float* __restrict__ wsrc, const int64_t* __restrict__ ids, int64_t N,
+                         int64_t L, float4* __restrict__ emb4, int* __restrict__ status) {
+  __shared__ float4 part[kEmbedWarps][NCH * 32];
+  __shared__ int part_cnt[kEmbedWarps];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  bool bad = false;
+  for (int64_t i = blockIdx.x; i < N; i += gridDim.x) {
+    float4 acc[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cnt = 0;
+    const int64_t* row_ids = ids + i * L;
+    const float* row_w = EXPLICIT_W ? wsrc + i * L : nullptr;
+    for (int64_t base = 32 * (int64_t)warp; base < L; base += 32 * kEmbedWarps)
+      cnt += accumulate_chunk<NCH, EXPLICIT_W>(acc, table4, V, d4, wsrc, row_ids, row_w, base, L,
+                                               lane, bad);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) part[warp][lane + 32 * c] = acc[c];
+    if (lane == 0) part_cnt[warp] = cnt;
+    __syncthreads();
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < kEmbedWarps; ++w) total += part_cnt[w];
+    const float div = (float)total;
+    for (int k = threadIdx.x; k < d4; k += blockDim.x) {
+      float4 s = part[0][k];
+#pragma unroll
+      for (int w = 1; w < kEmbedWarps; ++w) {
+        float4 p = part[w][k];
+        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+      }
+      s.x = __fdiv_rn(s.x, div); s.y = __fdiv_rn(s.y, div);
+      s.z = __fdiv_rn(s.z, div); s.w = __fdiv_rn(s.w, div);
+      st_stream(emb4 + (size_t)i * d4 + k, s);
+    }
+    __syncthreads();
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, MMB_STATUS_BAD_INDEX);
+}
+
+template <int NCH, bool EXPLICIT_W>
+static int launch_embed(const float* table, int64_t V, int d, const float* wsrc, const int64_t* ids,
+                        int64_t N, int64_t L, float* emb, int* status, cudaStream_t st) {
+  const int sms = sm_count();
+  const int d4 = d / 4;
+  const bool few_long = (L >= 256) && (N < (int64_t)sms * 16);
+  if (few_long) {
+    int grid = (int)(N < (int64_t)sms * 8 ? N : (int64_t)sms * 8);
+    sif_embed_cta_kernel<NCH, EXPLICIT_W><<<grid, kEmbedWarps * 32, 0, st>>>(
+        (const float4*)table, (int)V, d4, wsrc, ids, N, L, (float4*)emb, status);
+  } else {
+    // Persistent-style grid: a multiple of the SM count, grid-stride over utterances.
+    int64_t blocks = ceil_div(N, kEmbedWarps);
+    int64_t cap = (int64_t)sms * 8;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    sif_embed_warp_kernel<NCH, EXPLICIT_W><<<grid, kEmbedWarps * 32, 0, st>>>(
+        (const float4*)table, (int)V, d4, wsrc, ids, N, L, (float4*)emb, status);
+  }
+  MMB_LAUNCH_CHECK("sif_embed");
+  return MMB_OK;
+}
+
+template <bool EXPLICIT_W>
+static int dispatch_embed(const float* table, int64_t V, int d, const float* wsrc,
+                          const int64_t* ids, int64_t N, int64_t L, float* emb, int* status,
+                          cudaStream_t st) {
+  MMB_REQUIRE(table && wsrc && ids && emb && status, "null pointer");
+  MMB_REQUIRE(d > 0 && d % 4 == 0 && d <= 1024, "d must be a multiple of 4, <= 1024");
+  MMB_REQUIRE(V > 0 && V < (int64_t)1 << 31, "V out of range");
+  MMB_REQUIRE(N >= 0 && L >= 0, "negative size");
+  MMB_REQUIRE(((uintptr_t)table % 16 == 0) && ((uintptr_t)emb % 16 == 0), "table/emb must be 16-byte aligned");
+  if (N == 0) return MMB_OK;
+  const int nch = (d / 4 + 31) / 32;
+  switch (nch) {
+    case 1: return launch_embed<1, EXPLICIT_W>(table, V, d, wsrc, ids, N, L, emb, status, st);
+    case 2: return launch_embed<2, EXPLICIT_W>(table, V, d, wsrc, ids, N, L, emb, status, st);
+    case 3: return launch_embed<3, EXPLICIT_W>(table, V, d, wsrc, ids, N, L, emb, status, st);
+    case 4: return launch_embed<4, EXPLICIT_W>(table, V, d, wsrc, ids, N, L, emb, status, st);
+    default: return launch_embed<8, EXPLICIT_W>(table, V, d, wsrc, ids, N, L, emb, status, st);
+  }
+}
+
+}  // namespace mmb
+
+using namespace mmb;
+
+extern "C" int mmb_seq2weight(const int64_t* seq, const float* mask, const float* weight4ind,
+                              int64_t V, int64_t N, int64_t L, float* w, int* status,
+                              mmb_stream_t stream) {
+  MMB_REQUIRE(seq && weight4ind && w && status, "null pointer");
+  MMB_REQUIRE(N >= 0 && L >= 0 && V > 0, "bad size");
+  const int64_t n = N * L;
+  if (n == 0) return MMB_OK;
+  int64_t blocks = ceil_div(n, 256 * 4);
+  int64_t cap = (int64_t)sm_count() * 16;
+  int grid = (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+  seq2weight_kernel<<<grid, 256, 0, as_stream(stream)>>>(seq, mask, weight4ind, V, n, w, status);
+  MMB_LAUNCH_CHECK("seq2weight");
+  return MMB_OK;
+}
+
+extern "C" int mmb_weighted_average(const float* table, int64_t V, int d, const int64_t* x,
+                                    const float* w, int64_t N, int64_t L, float* emb, int* status,
+                                    mmb_stream_t stream) {
+  return dispatch_embed<true>(table, V, d, w, x, N, L, emb, status, as_stream(stream));
+}
+
+extern "C" int mmb_sif_embed(const float* table, int64_t V, int d, const float* vocab_w,
+                             const int64_t* x, int64_t N, int64_t L, float* emb, int* status,
+                             mmb_stream_t stream) {
+  return dispatch_embed<false>(table, V, d, vocab_w, x, N, L, emb, status, as_stream(stream));
+}

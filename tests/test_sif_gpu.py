@@ -1,0 +1,209 @@
+"""GPU parity of the SIF path (rows A1-A5) through the C ABI vs the CPU oracle and the
+reference-generated golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import sif_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+EMB_RTOL = 1e-5     # north_star: embeddings within 1e-5 relative
+PC_COS = 0.9999     # north_star: |cos| >= 0.9999 up to sign
+
+
+@pytest.fixture(scope='module')
+def mods():
+    import torch
+    import _native
+    import sif_functions
+    import sif
+    assert torch.cuda.is_available()
+    assert os.path.exists(_native.LIB_PATH)
+    return _native, sif_functions, sif
+
+
+def rel_err(got, want):
+    scale = np.abs(want).max(axis=-1, keepdims=True)
+    scale[scale == 0] = 1.0
+    return float(np.max(np.abs(got - want) / scale))
+
+
+def abs_cos(a, b):
+    return abs(float(np.dot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b))))
+
+
+@pytest.mark.parametrize('name', ['sif_mosi_like.npz', 'sif_tall.npz'])
+def test_golden_pipeline(mods, golden_dir, name):
+    nv, sf, sif = mods
+    g = np.load(os.path.join(golden_dir, name))
+    We, weights, ids = g['We'], g['weights'], g['ids']
+    w = sf.seq2weight(ids, np.ones(ids.shape), weights)
+    assert w.dtype == np.float32
+    np.testing.assert_array_equal(w, g['w'])                         # lookup: bit-exact
+    avg = sf.get_weighted_average(We, ids, w)
+    assert avg.dtype == np.float64 and avg.shape == (ids.shape[0], 300)
+    assert rel_err(avg[:64], g['avg']) < EMB_RTOL
+    pc = sf.compute_pc(avg, 1)
+    assert pc.shape == (1, 300) and pc.dtype == np.float64
+    assert float(np.dot(pc[0], g['pc'][0])) > PC_COS                 # sign convention too
+    emb = sif.get_sentence_embeddings(We, weights, ids)
+    assert emb.dtype == np.float64
+    assert rel_err(emb[:64], g['emb']) < 5 * EMB_RTOL
+    p = sf.Params()
+    p.rmpc = 1
+    emb2 = sf.SIF_embedding(We, ids, w, p)
+    assert rel_err(emb2[:64], g['emb']) < 5 * EMB_RTOL
+    p.rmpc = 0
+    assert rel_err(sf.SIF_embedding(We, ids, w, p)[:64], g['avg']) < EMB_RTOL
+
+
+def test_golden_pom_real_ids(mods, golden_dir):
+    """Real POM ids (8 x 1357, right-padded with id 0 whose weight is 1.0) + real weights."""
+    nv, sf, sif = mods
+    g = np.load(os.path.join(golden_dir, 'sif_pom_real.npz'))
+    ids = g['ids'].astype(np.int64)
+    We = cases.table(7763, 300, seed=11)
+    np.testing.assert_allclose(cases.checksum(We), g['table_sum'], rtol=1e-12)
+    w = sf.seq2weight(ids, np.ones(ids.shape), g['weights'])
+    np.testing.assert_array_equal(np.count_nonzero(w, axis=1), g['w_nonzero'])
+    np.testing.assert_allclose(w.sum(1), g['w_rowsum'], rtol=1e-6)
+    avg = sf.get_weighted_average(We, ids, w)                        # CTA-per-utterance kernel
+    assert rel_err(avg, g['avg']) < EMB_RTOL
+    emb = sif.get_sentence_embeddings(We, g['weights'], ids)
+    assert rel_err(emb, g['emb']) < 5 * EMB_RTOL
+
+
+@pytest.mark.parametrize('tag', list(cases.PC_CASES))
+@pytest.mark.parametrize('npc', [1, 2, 3])
+def test_compute_pc_matches_sklearn(mods, golden_dir, tag, npc):
+    nv, sf, sif = mods
+    g = np.load(os.path.join(golden_dir, 'pc_cases.npz'))
+    n, gap, seed = cases.PC_CASES[tag]
+    X = cases.pc_matrix(n, gap, seed)
+    pc = sf.compute_pc(X, npc)
+    want = g['%s_pc%d' % (tag, npc)]
+    assert pc.shape == want.shape
+    np.testing.assert_allclose(np.linalg.norm(pc, axis=1), 1.0, atol=1e-5)
+    for i in range(npc):
+        c = float(np.dot(pc[i], want[i]))
+        assert c > PC_COS, (tag, npc, i, c)
+    rm = sf.remove_pc(X, npc)
+    assert rm.dtype == np.float64
+    assert np.max(np.abs(rm[:16] - g['%s_rm%d' % (tag, npc)])) < 2e-4 * np.abs(X).max()
+
+
+@pytest.mark.parametrize('n,L,V,d', [(1, 1, 5, 300), (7, 33, 50, 300), (300, 64, 1000, 300),
+                                     (513, 20, 3016, 300), (40, 700, 400, 300), (65, 5, 30, 64),
+                                     (33, 9, 30, 512), (3, 300, 20, 128)])
+def test_embed_shapes_vs_oracle(mods, n, L, V, d):
+    """Ragged/edge shapes, both kernel variants (warp- and CTA-per-utterance), d != 300."""
+    nv, sf, sif = mods
+    rng = np.random.default_rng(n * 1000 + L)
+    We = cases.table(V, d, seed=n + L)
+    ids, p = cases.zipf_ids(rng, n, L, V)
+    weights = cases.sif_weights(p)
+    w = sf.seq2weight(ids, np.ones(ids.shape), weights)
+    np.testing.assert_array_equal(w, so.seq2weight(ids, np.ones(ids.shape), weights))
+    avg = sf.get_weighted_average(We, ids, w)
+    assert rel_err(avg, so.get_weighted_average(We, ids, w)) < EMB_RTOL
+
+
+def test_quirks(mods):
+    """Pad id counted in the divisor, negative ids, zero weights, all-zero rows, masks."""
+    nv, sf, sif = mods
+    rng = np.random.default_rng(5)
+    V, d = 40, 300
+    We = cases.table(V, d, seed=9)
+    weights = rng.uniform(0.1, 1.0, V)
+    weights[0] = 1.0
+    weights[7] = 0.0
+    ids = rng.integers(1, V, size=(6, 10)).astype(np.int64)
+    ids[0, 5:] = 0                     # padding counts: weight[0] = 1
+    ids[1, 2] = -1                     # negative id: weight 0, NumPy wraps the row read
+    ids[2, :] = 7                      # all weights zero -> 0/0 -> NaN row
+    ids[3, 0] = 7                      # zero-weight token does not count in the divisor
+    mask = np.ones(ids.shape)
+    mask[4, 3:] = 0                    # masked tokens get weight 0
+    w = sf.seq2weight(ids, mask, weights)
+    want_w = so.seq2weight(ids, mask, weights)
+    np.testing.assert_array_equal(w, want_w)
+    with np.errstate(all='ignore'):
+        want = so.get_weighted_average(We, ids, want_w)
+    got = sf.get_weighted_average(We, ids, w)
+    assert np.isnan(got[2]).all() and np.isnan(want[2]).all()
+    ok = [0, 1, 3, 4, 5]
+    assert rel_err(got[ok], want[ok]) < EMB_RTOL
+    # explicit non-zero weight on a negative id: NumPy indexes from the end of the table
+    w2 = w.copy()
+    w2[1, 2] = 0.5
+    assert rel_err(sf.get_weighted_average(We, ids, w2)[1:2], so.get_weighted_average(We, ids, w2)[1:2]) < EMB_RTOL
+
+
+def test_index_errors(mods):
+    nv, sf, sif = mods
+    We = cases.table(20, 300, seed=1)
+    weights = np.ones(20)
+    ids = np.array([[1, 2, 25]], dtype=np.int64)
+    with pytest.raises(IndexError):
+        sf.seq2weight(ids, np.ones(ids.shape), weights)
+    with pytest.raises(IndexError):
+        sf.get_weighted_average(We, ids, np.ones(ids.shape, np.float32))
+    with pytest.raises(IndexError):
+        sif.get_sentence_embeddings(We, weights, ids)
+    with pytest.raises(IndexError):
+        sf.get_weighted_average(We, np.array([[-21]], dtype=np.int64), np.ones((1, 1), np.float32))
+
+
+def test_empty_inputs(mods):
+    nv, sf, sif = mods
+    We = cases.table(20, 300, seed=1)
+    assert sf.seq2weight(np.zeros((0, 5), np.int64), np.ones((0, 5)), np.ones(20)).shape == (0, 5)
+    assert sf.get_weighted_average(We, np.zeros((0, 5), np.int64), np.zeros((0, 5), np.float32)).shape == (0, 300)
+
+
+def test_gram_fp32_matches_numpy(mods):
+    import torch
+    nv, sf, sif = mods
+    rng = np.random.default_rng(3)
+    for n in (1, 31, 300, 2199, 20000):
+        X = rng.standard_normal((n, 300)).astype(np.float32)
+        G = sf.gram(torch.as_tensor(X).cuda(), nv.GRAM_FP32).cpu().numpy()
+        want = X.astype(np.float64).T @ X.astype(np.float64)
+        assert np.max(np.abs(G - want)) < 2e-6 * np.abs(want).max() * max(1, np.sqrt(n) / 30)
+        np.testing.assert_array_equal(G, G.T)
+
+
+def test_large_properties_full_size_slice(mods):
+    """Size-independent properties at the bench shape (64 tokens, 400k vocab): after PC
+    removal every row is orthogonal to the component, removal is idempotent, and the device
+    path is bitwise deterministic."""
+    import torch
+    nv, sf, sif = mods
+    dev = torch.device('cuda')
+    g = torch.Generator(device=dev)
+    g.manual_seed(0)
+    V, d, n, L = 400_000, 300, 200_000, 64
+    table = 0.4 * torch.randn((V, d), device=dev, generator=g) + 0.3 * torch.randn((1, d), device=dev, generator=g)
+    table[0] = 0
+    u = torch.rand((n, L), device=dev, generator=g)
+    ids = (u.pow(6.0) * (V - 1)).long() + 1
+    lens = torch.randint(16, L + 1, (n, 1), device=dev, generator=g)
+    ids[torch.arange(L, device=dev)[None, :] >= lens] = 0
+    vw = torch.rand(V, device=dev, generator=g) * 0.9 + 0.1
+    vw[0] = 1.0
+    emb, pc = sf.sif_embedding_device(table, vw, ids, npc=1, return_pc=True)
+    emb_b, pc_b = sf.sif_embedding_device(table, vw, ids, npc=1, return_pc=True)
+    assert torch.equal(emb, emb_b) and torch.equal(pc, pc_b)
+    proj = (emb.double() @ pc.double().T).abs().max().item()
+    assert proj < 1e-4 * emb.abs().max().item()
+    again = sf.project_out(emb, pc)
+    assert (again - emb).abs().max().item() < 1e-5 * emb.abs().max().item()
+    # spot-check rows against the oracle
+    rows = torch.tensor([0, 1, 77777, n - 1], device=dev)
+    w_rows = vw[ids[rows]].cpu().numpy()
+    avg = so.get_weighted_average(table.cpu().numpy(), ids[rows].cpu().numpy(), w_rows)
+    want = so.remove_pc_with(avg, pc.double().cpu().numpy())
+    assert rel_err(emb[rows].double().cpu().numpy(), want) < 5 * EMB_RTOL
