@@ -45,7 +45,8 @@ int gram_tc(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_byte
 bool gram_tc_supported(int64_t N, int d);
 
 static int resolve_gram_mode(int64_t N, int d, int mode) {
-  if (mode == MMB_GRAM_AUTO) return gram_tc_supported(N, d) ? MMB_GRAM_TF32X3 : MMB_GRAM_FP32;
+  // small splits (MOSI / POM sizes) cannot fill a tensor-core pipeline: exact FP32 path
+  if (mode == MMB_GRAM_AUTO) return (N >= 4096 && gram_tc_supported(N, d)) ? MMB_GRAM_TF32X3 : MMB_GRAM_FP32;
   return mode;
 }
 

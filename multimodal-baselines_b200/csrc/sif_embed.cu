@@ -231,10 +231,11 @@ template <bool EXPLICIT_W>
 static int dispatch_embed(const float* table, int64_t V, int d, const float* wsrc,
                           const int64_t* ids, int64_t N, int64_t L, float* emb, int* status,
                           cudaStream_t st) {
-  MMB_REQUIRE(table && wsrc && ids && emb && status, "null pointer");
   MMB_REQUIRE(d > 0 && d % 4 == 0 && d <= 1024, "d must be a multiple of 4, <= 1024");
   MMB_REQUIRE(V > 0 && V < (int64_t)1 << 31, "V out of range");
   MMB_REQUIRE(N >= 0 && L >= 0, "negative size");
+  if (N == 0) return MMB_OK;   // empty input: nothing to do (pointers may be null)
+  MMB_REQUIRE(table && wsrc && emb && status && (ids || L == 0), "null pointer");
   MMB_REQUIRE(((uintptr_t)table % 16 == 0) && ((uintptr_t)emb % 16 == 0), "table/emb must be 16-byte aligned");
   if (N == 0) return MMB_OK;
   const int nch = (d / 4 + 31) / 32;
@@ -254,10 +255,10 @@ using namespace mmb;
 extern "C" int mmb_seq2weight(const int64_t* seq, const float* mask, const float* weight4ind,
                               int64_t V, int64_t N, int64_t L, float* w, int* status,
                               mmb_stream_t stream) {
-  MMB_REQUIRE(seq && weight4ind && w && status, "null pointer");
   MMB_REQUIRE(N >= 0 && L >= 0 && V > 0, "bad size");
   const int64_t n = N * L;
-  if (n == 0) return MMB_OK;
+  if (n == 0) return MMB_OK;   // empty input: nothing to do (pointers may be null)
+  MMB_REQUIRE(seq && weight4ind && w && status, "null pointer");
   int64_t blocks = ceil_div(n, 256 * 4);
   int64_t cap = (int64_t)sm_count() * 16;
   int grid = (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);

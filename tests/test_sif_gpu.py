@@ -207,3 +207,20 @@ def test_large_properties_full_size_slice(mods):
     avg = so.get_weighted_average(table.cpu().numpy(), ids[rows].cpu().numpy(), w_rows)
     want = so.remove_pc_with(avg, pc.double().cpu().numpy())
     assert rel_err(emb[rows].double().cpu().numpy(), want) < 5 * EMB_RTOL
+
+
+def test_gram_tcgen05_matches_float64(mods):
+    """3xTF32 tcgen05 Gram vs float64 and vs the FP32 CUDA-core kernel; ragged K tails."""
+    import torch
+    nv, sf, sif = mods
+    torch.manual_seed(1)
+    for n in (1, 15, 16, 17, 300, 4097, 150_001):
+        X = (0.4 * torch.randn(n, 300, device='cuda') + 0.3 * torch.randn(1, 300, device='cuda')).contiguous()
+        want = X.double().T @ X.double()
+        G = sf.gram(X, nv.GRAM_TF32X3)
+        scale = want.abs().max().item()
+        assert (G.double() - want).abs().max().item() < 2e-5 * scale, n
+        assert torch.equal(G, G.T)
+        assert torch.equal(G, sf.gram(X, nv.GRAM_TF32X3))            # deterministic
+        G32 = sf.gram(X, nv.GRAM_FP32)
+        assert (G - G32).abs().max().item() < 2e-5 * scale
