@@ -3,23 +3,30 @@
 // Reference: sif_functions.py:58-67 (compute_pc); the Gram is all that sklearn's randomized
 // SVD needs of X.  Specialised for d = 300.
 //
-// Data flow per CTA (persistent over a contiguous range of K = utterance rows):
+// Data flow per CTA (one per SM, persistent over a contiguous range of K = utterance rows):
 //   TMA      : X rows [k0, k0+16) arrive as ten 32-column boxes (cols 300..319 zero-filled by
-//              the TMA unit) in the canonical MN-major SWIZZLE_128B operand layout -- X is
-//              row-major (N, 300), i.e. "MN-major" for both operands of X^T X, so no
-//              transpose is ever needed: A = B = the same shared-memory tile.
-//   split    : 4 warps turn the FP32 tile into hi = x & 0xffffe000 (in place) and
-//              lo = x - hi (second buffer); element-wise, so swizzle-agnostic.
+//              the TMA unit) in the canonical MN-major operand layout for 32-bit types,
+//              SWIZZLE_128B with a 32-byte base (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B <->
+//              UMMA LayoutType 1, cute Swizzle<2,5,2>; the only MN-major layout tf32 accepts).
+//              X is row-major (N, 300), i.e. "MN-major" for both operands of X^T X, so no
+//              transpose is ever needed: A = B = the same shared-memory tile.  5-stage ring.
+//   workers  : 4 warps compute lo = x - trunc_tf32(x) into a second buffer (element-wise, so
+//              swizzle-agnostic).  The MMA ignores the low 13 mantissa bits of its FP32
+//              operands (verified bit-for-bit on B200), so "hi" is the raw TMA tile.
 //   MMA      : one elected thread issues tcgen05.mma (M = 128) for the upper-triangular blocks
 //                 tile A  rows   0..127 x cols   0..303   (N = 256 + 48)   TMEM cols   0..303
 //                 tile B  rows 128..255 x cols 128..303   (N = 176)        TMEM cols 304..479
-//              with three passes (lo*hi, hi*lo, hi*hi) per 8-row K step.
-//              The remaining 44x44 block (rows/cols 256..299) does not fit in the 512 TMEM
-//              columns next to A and B, so a few CTAs ("role C") run the same pipeline on
-//              the four boxes covering cols 192..319 only (A rows 192..319, N = 48).
-//   epilogue : TMEM -> registers (tcgen05.ld) -> per-CTA partial tile in global memory;
-//              a second kernel sums the partials in CTA order (deterministic) and mirrors
-//              the upper triangle.
+//              with three passes (lo*hi, hi*lo, hi*hi) per 8-row K step: 18 MMAs per stage.
+//   block C  : the remaining 44x44 block (rows/cols 256..299) does not fit in the 512 TMEM
+//              columns next to A and B (it would need 48 more), so the worker warps compute
+//              it on the CUDA cores in exact FP32 from the raw tile, 4x4 register blocks.
+//   flush    : the tensor core adds each MMA into the FP32 accumulator with truncation, a bias
+//              of ~1e-7 per MMA that grows linearly with the K chain (measured 1e-4 relative
+//              over 6.7 k rows); every `seg` stages (default 64 = 1024 rows) the workers drain
+//              TMEM (tcgen05.ld) into the CTA's FP32 partial tile in global memory with
+//              round-to-nearest adds, which bounds the bias at ~2e-5 relative.
+//   reduce   : a second kernel sums the per-CTA partials in CTA order (deterministic) and
+//              mirrors the upper triangle.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -30,15 +37,16 @@ namespace tc {
 
 constexpr int kD = 300;
 constexpr int kBK = 16;                         // X rows per pipeline stage
-constexpr int kStages = 4;
+constexpr int kStages = 5;
 constexpr int kBoxes = 10;                      // 32-column boxes (320 >= 300)
 constexpr int kBoxBytes = kBK * 128;            // one box: kBK rows x 128 B
 constexpr int kHiBytes = kBoxes * kBoxBytes;    // 20480
 constexpr int kStageBytes = 2 * kHiBytes;       // hi + lo
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kSegDefault = 64;                 // 1024 rows between TMEM flushes
 constexpr int kThreads = 192;                   // warp0 TMA, warp1 MMA, warps 2-5 split/epilogue
 constexpr int kColsAB = 480, kColsC = 48;
-constexpr int kPartialStride = 128 * kColsAB;   // floats per CTA partial (role C uses a prefix)
+constexpr int kPartialStride = 128 * kColsAB + kColsC * kColsC;   // floats per CTA: tiles A|B, then block C
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -71,15 +79,19 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// Shared-memory matrix descriptor, MN-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1, [61,64) layout = 2.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor, MN-major (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1, [61,64) layout type
+// (1 = SWIZZLE_128B_BASE32B).  Canonical layout in 16-byte units: ((8,n),(4,k)):((1,LBO),(8,SBO))
+// -- 32 floats contiguous along MN, 4 K rows of 128 B per swizzle atom, K atoms SBO apart,
+// 32-column MN blocks LBO apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = 1) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fff);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 at [4,6), a/b format
@@ -115,42 +127,46 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 struct Params {
   int64_t N;
-  int n_ab;           // CTAs [0, n_ab) run role AB, the rest role C
-  int n_c;
+  int n_cta;
   int passes;         // 3 = 3xTF32, 1 = plain TF32 (debug)
-  uint32_t lbo, sbo;  // descriptor strides in bytes (runtime so a bring-up sweep can vary them)
+  int seg;            // K blocks accumulated in TMEM between two flushes to the FP32 partial
+  int prefetch;       // K blocks of L2 prefetch distance (0 = off)
+  uint32_t lbo, sbo;  // descriptor strides in bytes
   float* partial;
 };
+
+__device__ __forceinline__ uint64_t desc_at(uint64_t base, uint32_t saddr) {
+  return base | (uint64_t)((saddr >> 4) & 0x3fff);
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
     gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params prm) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + kStages * kStageBytes);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * kStages + 1);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * kStages + 2);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_full = smem_u32(bars), bar_ready = bar_full + 8 * kStages,
-                 bar_empty = bar_ready + 8 * kStages, bar_done = bar_empty + 8 * kStages;
+                 bar_empty = bar_ready + 8 * kStages, bar_done = bar_empty + 8 * kStages,
+                 bar_free = bar_done + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const bool role_c = (int)blockIdx.x >= prm.n_ab;
-  const int role_rank = role_c ? blockIdx.x - prm.n_ab : blockIdx.x;
-  const int role_size = role_c ? prm.n_c : prm.n_ab;
   const int64_t kblocks = (prm.N + kBK - 1) / kBK;
-  const int64_t per = (kblocks + role_size - 1) / role_size;
-  const int64_t kb0 = role_rank * per;
+  const int64_t per = (kblocks + prm.n_cta - 1) / prm.n_cta;
+  const int64_t kb0 = (int64_t)blockIdx.x * per;
   int64_t kb1 = kb0 + per;
   if (kb1 > kblocks) kb1 = kblocks;
   const int64_t nkb = kb1 > kb0 ? kb1 - kb0 : 0;
-  const int box0 = role_c ? 6 : 0, nbox = role_c ? 4 : kBoxes;
+  const int64_t nseg = (nkb + prm.seg - 1) / prm.seg;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_ready + 8 * s, 4);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 5);   // MMA commit + the four worker warps (block C reads)
     }
     mbar_init(bar_done, 1);
+    mbar_init(bar_free, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -169,12 +185,18 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int64_t i = 0; i < nkb; ++i) {
         const int s = (int)(i % kStages);
         const uint32_t ph = (uint32_t)((i / kStages) & 1);
+        if (prm.prefetch > 0 && i + prm.prefetch < nkb) {   // warm L2 ahead of the ring
+          const int prow = (int)((kb0 + i + prm.prefetch) * kBK);
+          for (int b = 0; b < kBoxes; ++b)
+            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmap),
+                         "r"(b * 32), "r"(prow) : "memory");
+        }
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        mbar_expect_tx(bar_full + 8 * s, (uint32_t)(nbox * kBoxBytes));
+        mbar_expect_tx(bar_full + 8 * s, (uint32_t)kHiBytes);
         const uint32_t dst = smem_base + s * kStageBytes;
         const int row = (int)((kb0 + i) * kBK);
-        for (int b = 0; b < nbox; ++b)
-          tma_load_2d(dst + (box0 + b) * kBoxBytes, &tmap, (box0 + b) * 32, row, bar_full + 8 * s);
+        for (int b = 0; b < kBoxes; ++b)
+          tma_load_2d(dst + b * kBoxBytes, &tmap, b * 32, row, bar_full + 8 * s);
       }
     }
   } else if (warp == 1) {
@@ -183,86 +205,144 @@ __global__ void __launch_bounds__(kThreads, 1)
       constexpr uint32_t idesc256 = make_idesc(128, 256), idesc48 = make_idesc(128, 48),
                          idesc176 = make_idesc(128, 176);
       const uint32_t blk = prm.lbo;  // byte distance between 32-column blocks
-      for (int64_t i = 0; i < nkb; ++i) {
-        const int s = (int)(i % kStages);
-        const uint32_t ph = (uint32_t)((i / kStages) & 1);
-        mbar_wait(bar_ready + 8 * s, ph);
-        tc_fence_after();
-        const uint32_t hi = smem_base + s * kStageBytes, lo = hi + kHiBytes;
-        for (int ks = 0; ks < kBK / 8; ++ks) {
-          const uint32_t koff = ks * 1024;  // one 8-row K group = 8 x 128 B
-          for (int p = 0; p < prm.passes; ++p) {
-            // passes: small terms first; the last pass is hi*hi
-            const uint32_t abase = (prm.passes == 3 && p == 0) ? lo : hi;
-            const uint32_t bbase = (prm.passes == 3 && p == 1) ? lo : hi;
-            const uint32_t acc = (i > 0 || ks > 0 || p > 0) ? 1u : 0u;
-            if (!role_c) {
-              const uint64_t a0 = make_desc(abase + koff, prm.lbo, prm.sbo);
-              const uint64_t a4 = make_desc(abase + 4 * blk + koff, prm.lbo, prm.sbo);
-              const uint64_t b0 = make_desc(bbase + koff, prm.lbo, prm.sbo);
-              const uint64_t b8 = make_desc(bbase + 8 * blk + koff, prm.lbo, prm.sbo);
-              const uint64_t b4 = make_desc(bbase + 4 * blk + koff, prm.lbo, prm.sbo);
+      const uint64_t dbase = make_desc(0, prm.lbo, prm.sbo);
+      int64_t i = 0;
+      for (int64_t sg = 0; sg < nseg; ++sg) {
+        if (sg > 0) {   // the workers have drained the accumulators of the previous segment
+          mbar_wait(bar_free, (uint32_t)((sg - 1) & 1));
+          tc_fence_after();
+        }
+        int64_t iend = i + prm.seg;
+        if (iend > nkb) iend = nkb;
+        bool first = true;
+        for (; i < iend; ++i) {
+          const int s = (int)(i % kStages);
+          const uint32_t ph = (uint32_t)((i / kStages) & 1);
+          mbar_wait(bar_ready + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t hi = smem_base + s * kStageBytes, lo = hi + kHiBytes;
+#pragma unroll
+          for (int ks = 0; ks < kBK / 8; ++ks) {
+            const uint32_t koff = ks * 1024;  // 8 K rows = two 4-row swizzle atoms of 512 B
+            for (int p = 0; p < prm.passes; ++p) {
+              // small terms first (lo*hi, hi*lo), then hi*hi; the MMA ignores the low 13
+              // mantissa bits of its FP32 operands, so "hi" is the raw TMA tile.
+              const uint32_t abase = ((prm.passes == 3 && p == 0) ? lo : hi) + koff;
+              const uint32_t bbase = ((prm.passes == 3 && p == 1) ? lo : hi) + koff;
+              const uint32_t acc = (first && ks == 0 && p == 0) ? 0u : 1u;
+              const uint64_t a0 = desc_at(dbase, abase), a4 = desc_at(dbase, abase + 4 * blk);
+              const uint64_t b0 = desc_at(dbase, bbase), b4 = desc_at(dbase, bbase + 4 * blk),
+                             b8 = desc_at(dbase, bbase + 8 * blk);
               umma_tf32(tmem + 0, a0, b0, idesc256, acc);     // rows 0..127   x cols 0..255
               umma_tf32(tmem + 256, a0, b8, idesc48, acc);    // rows 0..127   x cols 256..303
               umma_tf32(tmem + 304, a4, b4, idesc176, acc);   // rows 128..255 x cols 128..303
-            } else {
-              const uint64_t a6 = make_desc(abase + 6 * blk + koff, prm.lbo, prm.sbo);
-              const uint64_t b8 = make_desc(bbase + 8 * blk + koff, prm.lbo, prm.sbo);
-              umma_tf32(tmem + 0, a6, b8, idesc48, acc);      // rows 192..319 x cols 256..303
             }
           }
+          first = false;
+          umma_commit(bar_empty + 8 * s);   // frees the stage when these MMAs have read it
         }
-        umma_commit(bar_empty + 8 * s);   // frees the stage when these MMAs have read it
+        umma_commit(bar_done);              // this segment's accumulators are complete
       }
-      umma_commit(bar_done);              // accumulators complete
     }
   } else {
-    // ===== split (hi/lo) workers, then epilogue =====
+    // ===== workers: lo = x - trunc_tf32(x); block C (rows/cols 256..299) in FP32; flushes =====
     const int t = threadIdx.x - 64;  // 0..127
-    for (int64_t i = 0; i < nkb; ++i) {
-      const int s = (int)(i % kStages);
-      const uint32_t ph = (uint32_t)((i / kStages) & 1);
-      mbar_wait(bar_full + 8 * s, ph);
-      float4* hi = (float4*)(smem + s * kStageBytes + box0 * kBoxBytes);
-      float4* lo = (float4*)(smem + s * kStageBytes + kHiBytes + box0 * kBoxBytes);
-      const int n16 = nbox * kBoxBytes / 16;
-      for (int e = t; e < n16; e += 128) {
-        const float4 x = hi[e];
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-        h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-        h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-        h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-        l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
-        hi[e] = h;
-        lo[e] = l;
-      }
-      fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_ready + 8 * s);
-    }
-    // epilogue: this warp may touch TMEM lanes [32*(warp%4), +32)
-    if (nkb > 0) {
-      mbar_wait(bar_done, 0);
-      tc_fence_after();
-    }
-    const int q = warp & 3;
+    const int q = warp & 3;          // TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;
-    float* out = prm.partial + (size_t)blockIdx.x * kPartialStride + (size_t)row * (role_c ? kColsC : kColsAB);
-    const int ncols = role_c ? kColsC : kColsAB;
-    if (nkb > 0) {
-      for (int c = 0; c < ncols; c += 32) {
+    float* part = prm.partial + (size_t)blockIdx.x * kPartialStride;
+    float* out = part + (size_t)row * kColsAB;
+    // block C: 11 x 11 grid of 4x4 blocks over cols 256..299, upper triangle (66 pairs),
+    // dealt round-robin to the four warps.
+    const int pidx = lane * 4 + (warp - 2);
+    int ti = 0, tj = 0;
+    const bool has_c = pidx < 66;
+    if (has_c) {
+      int r = pidx;
+      while (r >= 11 - ti) { r -= 11 - ti; ++ti; }
+      tj = ti + r;
+    }
+    float cacc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) cacc[a][b] = 0.f;
+    const int ca = 4 * ti, cb = 4 * tj;   // column offsets inside [256, 300)
+    const uint32_t offa = (8 + (ca >> 5)) * kBoxBytes + (ca & 7) * 4, cha = (ca & 31) >> 3;
+    const uint32_t offb = (8 + (cb >> 5)) * kBoxBytes + (cb & 7) * 4, chb = (cb & 31) >> 3;
+
+    int64_t i = 0;
+    for (int64_t sg = 0; sg < nseg; ++sg) {
+      int64_t iend = i + prm.seg;
+      if (iend > nkb) iend = nkb;
+      for (; i < iend; ++i) {
+        const int s = (int)(i % kStages);
+        const uint32_t ph = (uint32_t)((i / kStages) & 1);
+        mbar_wait(bar_full + 8 * s, ph);
+        const uint8_t* stage = smem + s * kStageBytes;
+        const float4* hi = (const float4*)stage;
+        float4* lo = (float4*)(stage + kHiBytes);
+#pragma unroll
+        for (int e = 0; e < kHiBytes / 16 / 128; ++e) {
+          const float4 x = hi[t + 128 * e];
+          float4 l;
+          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          lo[t + 128 * e] = l;
+        }
+        fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ready + 8 * s);
+        if (has_c) {
+#pragma unroll
+          for (int k = 0; k < kBK; ++k) {
+            // 32-byte chunk index is XOR-swizzled with (row & 3)  (SWIZZLE_128B_ATOM_32B)
+            const float4 a = *(const float4*)(stage + offa + k * 128 + ((cha ^ (k & 3)) << 5));
+            const float4 b = *(const float4*)(stage + offb + k * 128 + ((chb ^ (k & 3)) << 5));
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int v = 0; v < 4; ++v) cacc[u][v] = fmaf(av[u], bv[v], cacc[u][v]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+      }
+      // flush this segment's TMEM accumulators into the FP32 partial (round-to-nearest adds)
+      mbar_wait(bar_done, (uint32_t)(sg & 1));
+      tc_fence_after();
+      for (int c = 0; c < kColsAB; c += 32) {
         uint32_t r[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c, r);
-        const int w = (ncols - c) < 32 ? (ncols - c) : 32;
+        float4* o4 = (float4*)(out + c);
+        if (sg == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          if (j < w)
-            *(float4*)(out + c + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          for (int j = 0; j < 8; ++j)
+            o4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        } else {
+          float4 old[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) old[j] = o4[j];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o4[j] = make_float4(old[j].x + __uint_as_float(r[4 * j]), old[j].y + __uint_as_float(r[4 * j + 1]),
+                                old[j].z + __uint_as_float(r[4 * j + 2]), old[j].w + __uint_as_float(r[4 * j + 3]));
+        }
       }
-    } else {
-      for (int c = 0; c < ncols; c += 4) *(float4*)(out + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_free);
+    }
+    if (nseg == 0)
+      for (int c = 0; c < kColsAB; c += 4) *(float4*)(out + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_c) {
+      float* cpart = part + 128 * kColsAB;   // 48 x 48 block-C region
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        *(float4*)(cpart + (ca + u) * kColsC + cb) = make_float4(cacc[u][0], cacc[u][1], cacc[u][2], cacc[u][3]);
     }
   }
   tc_fence_before();
@@ -272,24 +352,19 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
-// G[i][j] = G[j][i] = sum over the CTAs of the owning role, in CTA order.
+// G[i][j] = G[j][i] = sum of the per-CTA partials in CTA order (deterministic).
 __global__ void __launch_bounds__(256)
-    gram_tc_reduce_kernel(const float* __restrict__ partial, int n_ab, int n_c, float* __restrict__ G) {
+    gram_tc_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ G) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= kD * kD) return;
   const int i = idx / kD, j = idx % kD;
   if (j < i) return;
+  const float* p;
+  if (i < 128) p = partial + (size_t)i * kColsAB + j;
+  else if (i < 256) p = partial + (size_t)(i - 128) * kColsAB + 304 + (j - 128);
+  else p = partial + 128 * kColsAB + (size_t)(i - 256) * kColsC + (j - 256);
   float s = 0.f;
-  if (i < 128) {
-    const float* p = partial + (size_t)i * kColsAB + j;
-    for (int c = 0; c < n_ab; ++c) s += p[(size_t)c * kPartialStride];
-  } else if (i < 256) {
-    const float* p = partial + (size_t)(i - 128) * kColsAB + 304 + (j - 128);
-    for (int c = 0; c < n_ab; ++c) s += p[(size_t)c * kPartialStride];
-  } else {
-    const float* p = partial + (size_t)n_ab * kPartialStride + (size_t)(i - 192) * kColsC + (j - 256);
-    for (int c = 0; c < n_c; ++c) s += p[(size_t)c * kPartialStride];
-  }
+  for (int c = 0; c < n_cta; ++c) s += p[(size_t)c * kPartialStride];
   G[(size_t)i * kD + j] = s;
   G[(size_t)j * kD + i] = s;
 }
@@ -310,17 +385,10 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static void plan(int64_t N, int* n_ab, int* n_c) {
-  const int sms = sm_count();
+static int plan(int64_t N) {
   const int64_t kblocks = (N + kBK - 1) / kBK;
-  int c = (int)(sms * 0.14 + 0.5);   // role C costs ~1/7 of role AB per K block (smem-bound estimate)
-  if (c < 1) c = 1;
-  int ab = sms - c;
-  if (ab < 1) ab = 1;
-  if (kblocks < ab) ab = (int)kblocks;
-  if (kblocks < c) c = (int)kblocks;
-  *n_ab = ab;
-  *n_c = c;
+  const int sms = sm_count();
+  return (int)(kblocks < sms ? (kblocks > 0 ? kblocks : 1) : sms);
 }
 
 }  // namespace tc
@@ -339,17 +407,14 @@ bool gram_tc_supported(int64_t N, int d) {
 
 size_t gram_tc_workspace_bytes(int64_t N, int d) {
   (void)d;
-  int ab, c;
-  tc::plan(N, &ab, &c);
-  return (size_t)(ab + c) * tc::kPartialStride * sizeof(float);
+  return (size_t)tc::plan(N) * tc::kPartialStride * sizeof(float);
 }
 
 int gram_tc(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_bytes, cudaStream_t st) {
   using namespace tc;
   MMB_REQUIRE(d == kD, "tcgen05 Gram is specialised for d == 300");
   MMB_REQUIRE(N < ((int64_t)1 << 31) - 64, "N too large for 32-bit TMA coordinates");
-  int n_ab, n_c;
-  plan(N, &n_ab, &n_c);
+  const int n_cta = plan(N);
   MMB_REQUIRE(ws_bytes >= gram_tc_workspace_bytes(N, d), "workspace too small");
   EncodeTiledFn enc = encode_fn();
   if (!enc) {
@@ -362,7 +427,7 @@ int gram_tc(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_byte
   const cuuint32_t box[2] = {32, (cuuint32_t)kBK};
   const cuuint32_t estride[2] = {1, 1};
   CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)X, gdim, gstride, box, estride,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("gram_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -375,18 +440,19 @@ int gram_tc(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_byte
   }
   Params prm;
   prm.N = N;
-  prm.n_ab = n_ab;
-  prm.n_c = n_c;
+  prm.n_cta = n_cta;
   prm.passes = 3;
+  prm.seg = kSegDefault;
+  prm.prefetch = 0;     // measured: L2 prefetch ahead of the 5-stage ring does not help
   prm.lbo = kBoxBytes;  // 32-column blocks are kBK*128 bytes apart
-  prm.sbo = 1024;       // 8-row K groups are 1024 bytes apart
+  prm.sbo = 512;        // 4-row K atoms (4 x 128 B) are 512 bytes apart
   if (const char* e = getenv("MMB_TC_PASSES")) prm.passes = atoi(e) == 1 ? 1 : 3;
-  if (const char* e = getenv("MMB_TC_LBO")) prm.lbo = (uint32_t)atoi(e);
-  if (const char* e = getenv("MMB_TC_SBO")) prm.sbo = (uint32_t)atoi(e);
+  if (const char* e = getenv("MMB_TC_SEG")) prm.seg = atoi(e) > 0 ? atoi(e) : kSegDefault;
+  if (const char* e = getenv("MMB_TC_PREFETCH")) prm.prefetch = atoi(e);
   prm.partial = (float*)ws;
-  gram_tc_kernel<<<n_ab + n_c, kThreads, kSmemBytes, st>>>(tmap, prm);
+  gram_tc_kernel<<<n_cta, kThreads, kSmemBytes, st>>>(tmap, prm);
   MMB_LAUNCH_CHECK("gram_tc");
-  gram_tc_reduce_kernel<<<(kD * kD + 255) / 256, 256, 0, st>>>((const float*)ws, n_ab, n_c, G);
+  gram_tc_reduce_kernel<<<(kD * kD + 255) / 256, 256, 0, st>>>((const float*)ws, n_cta, G);
   MMB_LAUNCH_CHECK("gram_tc_reduce");
   return MMB_OK;
 }

@@ -104,14 +104,14 @@ def start_block(n_rows, npc, seed=0):
     return np.random.RandomState(seed).normal(size=(int(n_rows), int(npc) + 10))
 
 
-def gram(X_t, mode=nv.GRAM_AUTO):
+def gram(X_t, mode=nv.GRAM_AUTO, return_ws=False):
     """``G = X^T X`` (d, d) float32 on the device (first half of compute_pc)."""
     n, d = X_t.shape
     G = torch.empty((d, d), dtype=torch.float32, device=X_t.device)
     nbytes = lib.mmb_gram_workspace_bytes(n, d, mode)
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=X_t.device)
     nv.check(lib.mmb_gram(nv.ptr(X_t), n, d, nv.ptr(G), nv.ptr(ws), nbytes, mode, nv.stream_ptr()))
-    return G
+    return (G, ws) if return_ws else G
 
 
 def pc_from_gram(G_t, npc, n_rows, X_t=None, S0_t=None, n_iter=7):
