@@ -134,38 +134,49 @@ MMB_API int mmb_sif_embedding_host(const float* table_dev, int64_t V, int d, con
                            float* pc_host, int gram_mode, int64_t chunk_rows);
 
 /* ---------------------------------------------------------------- MMB (A6-A9) ----- */
+/* In this section the pointer tables (W, b, out, seg_val ...) are HOST arrays of DEVICE
+ * pointers; the library copies them into kernel parameters (<= 16 heads, <= 8 modalities of
+ * <= 4 segments each).                                                                  */
 
 /* AudioVisualGeneratorMultimodal.forward -- models.py:187-202, all heads in one launch.
- * z (B, d) is the (already normalised) latent batch.  Head h (h < n_heads) has weight
- * W[h] (D[h], d) and bias b[h] (D[h]); heads come in (mu, log_sigma) pairs per modality
- * and `is_log_sigma[h]` selects the exp() epilogue.  out[h] is (B, D[h]).
- * Pointer tables are DEVICE arrays of device pointers.                                 */
+ * z (B, d) is the (already normalised) latent batch.  Head h has weight W[h] (D[h], d) and
+ * bias b[h] (D[h]) (nn.Linear layout); is_log_sigma[h] != 0 selects the exp() epilogue
+ * (sigma = exp(.), models.py:199).  out[h] is (B, D[h]).                                */
 MMB_API int mmb_heads_forward(const float* z, int B, int d, int n_heads, const float* const* W,
                       const float* const* b, const int* D, const int* is_log_sigma,
-                      float* const* out, int max_D, mmb_stream_t stream);
+                      float* const* out, mmb_stream_t stream);
+/* Backward of the above given gout[h] (B, D[h]) = d loss / d pre-activation of head h:
+ * dz (B, d) = sum_h gout[h] W[h];  dW[h] (D[h], d) = gout[h]^T z;  db[h] (D[h]) = column sums.
+ * dz, dW, db may be NULL (frozen heads, reference models.py:173-178).                   */
+MMB_API int mmb_heads_backward(const float* z, int B, int d, int n_heads, const float* const* W,
+                       const int* D, const float* const* gout, float* dz, float* const* dW,
+                       float* const* db, mmb_stream_t stream);
 
-/* get_normal_log_prob -- losses.py:13-34, for every modality of MMB1/MMB2 at once,
- * forward and the analytic gradients, reading each base tensor
- * (text_gauss, audio, visual) and its 0/1 float mask exactly once instead of the
- * concatenations of simplesif.py:94-113.
- *   base[s]  (B, T, F[s]) values, bmask[s] same shape, s in {0:text, 1:audio, 2:visual};
- *   modality m is the concatenation of the bases whose bit is set in mod_bases[m]
- *   (bit s = base s), in base order, like the reference's torch.cat;
- *   mu[m], log_sigma[m]: (B, Dm) with Dm = sum of its bases' F;
- *   lp (n_mod, B) log-likelihoods; dmu[m], dls[m] (B, Dm) = d lp[m] / d mu, d log_sigma.
- * `status` gets MMB_STATUS_NONFINITE if any lp is not finite (losses.py:258-264).      */
-MMB_API int mmb_gauss_ll(const float* const* base, const float* const* bmask, const int* F, int B, int T,
-                 int n_mod, const int* mod_bases, const float* const* mu,
-                 const float* const* log_sigma, float* lp, float* const* dmu, float* const* dls,
+/* get_normal_log_prob -- losses.py:13-34 for n_mod modalities in ONE launch: value and the
+ * analytic gradients.  Modality m is the concatenation along the
+ * feature axis (the torch.cat of simplesif.py:94-113, never materialised) of n_seg[m]
+ * segments; segments are listed modality after modality in seg_val / seg_mask / seg_F:
+ *   seg_val[s], seg_mask[s]: (B, T, seg_F[s]) values and float mask;
+ *   mu[m], sigma[m]: (B, D_m), D_m = sum of the modality's seg_F;
+ *   lp: (n_mod, B) = sum_{t,f} mask * (log(1/sqrt(2 pi sigma^2)) - (x-mu)^2 / (2 sigma^2));
+ *   dmu[m], dsigma[m]: (B, D_m) = d lp[m] / d mu, d sigma (tables or entries may be NULL).
+ * `status` gets MMB_STATUS_NONFINITE if any lp is not finite (losses.py:258-264).        */
+MMB_API int mmb_gauss_ll(int B, int T, int n_mod, const int* n_seg, const float* const* seg_val,
+                 const float* const* seg_mask, const int* seg_F, const float* const* mu,
+                 const float* const* sigma, float* lp, float* const* dmu, float* const* dsigma,
                  int* status, mmb_stream_t stream);
 
-/* get_word_log_prob_angular2 -- losses.py:68-95 forward + d/d latents (Appendix A.5).
- *   latents (B, d); table (V, d) and its per-row inverse norms inv_norm (V) (constant
- *   across steps: mmb_row_inv_norm); sent (B, L, d) token vectors, word_w (B, L),
- *   tmask (B, L) = mask[:, :, 0]; a = 1e-3 (simplesif.py:513).
- *   lp (B) and grad (B, d) = d lp / d latents.  ws >= mmb_word_ll_workspace_bytes(B, V). */
-MMB_API int mmb_row_inv_norm(const float* table, int64_t V, int d, float* inv_norm, mmb_stream_t stream);
-MMB_API size_t mmb_word_ll_workspace_bytes(int B, int64_t V, int L);
+/* get_word_log_prob_angular2 -- losses.py:68-95, value + d/d latents (Appendix A.5).
+ *   latents (B, d); table (V, d) and inv_norm (V) = 1/max(||row||, 1e-8) from
+ *   mmb_row_inv_norm (torch CosineSimilarity's clamp); sent: token vectors, element
+ *   (b, t, k) at sent[b*sent_stride_b + t*sent_stride_t + k]; word_w (B, L) dense; tmask
+ *   element (b, t) at tmask[b*tmask_stride_b + t*tmask_stride_t] (= mask[:, :, 0]);
+ *   a = 1e-3 (simplesif.py:513).  lp (B); grad (B, d) = d lp / d latents.
+ *   The partition term is a (B, d) x (d, V) product with an acos epilogue and its gradient a
+ *   (B, V) x (V, d) product -- no (B, V, d) broadcast temporaries.
+ *   ws >= mmb_word_ll_workspace_bytes(B, V, d).                                          */
+MMB_API int mmb_row_inv_norm(const float* X, int64_t n, int d, float* inv_norm, mmb_stream_t stream);
+MMB_API size_t mmb_word_ll_workspace_bytes(int B, int64_t V, int d);
 MMB_API int mmb_word_ll(const float* latents, int B, int d, const float* table, const float* inv_norm,
                 int64_t V, const float* sent, int64_t sent_stride_b, int64_t sent_stride_t,
                 const float* word_w, const float* tmask, int64_t tmask_stride_b,

@@ -46,8 +46,9 @@ SIGNATURES = {
     'mmb_sif_workspace_bytes': (_sz, [_i64, _i, _i]),
     'mmb_sif_embedding': (_i, [_p, _i64, _i, _p, _p, _i64, _i64, _i, _p, _p, _p, _p, _p, _sz, _i, _p, _p]),
     'mmb_sif_embedding_host': (_i, [_p, _i64, _i, _p, _p, _i64, _i64, _i, _p, _p, _i, _p, _i, _i64]),
-    'mmb_heads_forward': (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
-    'mmb_gauss_ll': (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'mmb_heads_forward': (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    'mmb_heads_backward': (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    'mmb_gauss_ll': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'mmb_row_inv_norm': (_i, [_p, _i64, _i, _p, _p]),
     'mmb_word_ll_workspace_bytes': (_sz, [_i, _i64, _i]),
     'mmb_word_ll': (_i, [_p, _i, _i, _p, _p, _i64, _p, _i64, _i64, _p, _p, _i64, _i64, _i, _f, _p, _p,

@@ -1,31 +1,509 @@
-// MMB likelihood step kernels (heads, masked Gaussian log-likelihood, angular word term).
-// Placeholders: the entry points exist so that the ABI is complete; they report
-// MMB_E_UNSUPPORTED until the kernels land.
+// MMB likelihood step:
+//   * generator heads   -- reference models.py:187-202  (mu = z W^T + b, sigma = exp(z W'^T + b'))
+//   * masked Gaussian    -- reference losses.py:13-34    (get_normal_log_prob), value + gradients
+//   * angular word term  -- reference losses.py:68-95    (get_word_log_prob_angular2), value + d/d latents
+// One step works on a minibatch of B = 64 utterances (512 for valid/test), so every kernel
+// here is launch/latency bound rather than bandwidth bound; the design goal is FEW launches
+// that read each input once (all heads in one launch, all modalities in one launch, no
+// torch.cat of the base tensors, no (B, V, d) broadcast temporaries), FP32 throughout.
+#include <math.h>
+
 #include "common.cuh"
+
+namespace mmb {
+
+constexpr int kMaxHeads = 16;
+constexpr int kMaxMods = 8;
+constexpr int kMaxSegs = 4;
+
+// --------------------------------------------------------------------------------------
+// 64x64 output tile of C = A * B with arbitrary element strides, FP32 FMA, 256 threads,
+// 4x4 register block per thread.  A(m,k) = A[m*a_rs + k*a_cs], B(k,n) = Bm[k*b_rs + n*b_cs].
+// Operand tiles go through shared memory transposed to [k][m] / [k][n] so that the inner
+// product reads two float4 per k.  Small-matrix helper: the problems here are <= 512 x 3016 x 425.
+// --------------------------------------------------------------------------------------
+constexpr int kTM = 64, kTN = 64, kTK = 16;
+
+struct TileSmem {
+  float a[kTK][kTM + 4];
+  float b[kTK][kTN + 4];
+};
+
+__device__ __forceinline__ void tile_gemm_accum(TileSmem& sm, float (&acc)[4][4], const float* __restrict__ A,
+                                                int64_t a_rs, int64_t a_cs, const float* __restrict__ Bm,
+                                                int64_t b_rs, int64_t b_cs, int m0, int n0, int M, int N, int K) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int k0 = 0; k0 < K; k0 += kTK) {
+    // stage: 64 x 16 elements of each operand, 4 per thread
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + 256 * e;          // 0..1023
+      {
+        // A: make the fastest-varying thread index follow the smaller stride
+        const int mm = (a_cs <= a_rs) ? idx / kTK : idx % kTM;
+        const int kk = (a_cs <= a_rs) ? idx % kTK : idx / kTM;
+        const int m = m0 + mm, k = k0 + kk;
+        sm.a[kk][mm] = (m < M && k < K) ? __ldg(A + m * a_rs + k * a_cs) : 0.f;
+      }
+      {
+        const int nn = (b_rs <= b_cs) ? idx / kTK : idx % kTN;
+        const int kk = (b_rs <= b_cs) ? idx % kTK : idx / kTN;
+        const int n = n0 + nn, k = k0 + kk;
+        sm.b[kk][nn] = (n < N && k < K) ? __ldg(Bm + k * b_rs + n * b_cs) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kTK; ++kk) {
+      const float4 a = *(const float4*)&sm.a[kk][ty * 4];
+      const float4 b = *(const float4*)&sm.b[kk][tx * 4];
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void zero_acc(float (&acc)[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+}
+
+// ---------------------------------------------------------------- heads (A6) ---------
+struct HeadsArgs {
+  const float* W[kMaxHeads];
+  const float* b[kMaxHeads];
+  float* out[kMaxHeads];
+  const float* gout[kMaxHeads];
+  float* dW[kMaxHeads];
+  float* db[kMaxHeads];
+  int D[kMaxHeads];
+  int is_ls[kMaxHeads];
+  int n_heads;
+};
+
+// out[h][m][n] = act(sum_k z[m][k] W[h][n][k] + b[h][n]); grid (n tiles, m tiles, heads)
+__global__ void __launch_bounds__(256)
+    heads_fwd_kernel(const float* __restrict__ z, int B, int d, const __grid_constant__ HeadsArgs args) {
+  __shared__ TileSmem sm;
+  const int h = blockIdx.z, D = args.D[h];
+  const int n0 = blockIdx.x * kTN, m0 = blockIdx.y * kTM;
+  if (n0 >= D) return;
+  float acc[4][4];
+  zero_acc(acc);
+  tile_gemm_accum(sm, acc, z, d, 1, args.W[h], 1, d, m0, n0, B, D, d);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const bool ls = args.is_ls[h] != 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= B) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= D) continue;
+      float v = acc[i][j] + __ldg(args.b[h] + n);
+      args.out[h][(size_t)m * D + n] = ls ? expf(v) : v;
+    }
+  }
+}
+
+// dz[m][n] = sum_h sum_k gout[h][m][k] W[h][k][n]; grid (n tiles over d, m tiles)
+__global__ void __launch_bounds__(256)
+    heads_bwd_dz_kernel(float* __restrict__ dz, int B, int d, const __grid_constant__ HeadsArgs args) {
+  __shared__ TileSmem sm;
+  const int n0 = blockIdx.x * kTN, m0 = blockIdx.y * kTM;
+  float acc[4][4];
+  zero_acc(acc);
+  for (int h = 0; h < args.n_heads; ++h)
+    tile_gemm_accum(sm, acc, args.gout[h], args.D[h], 1, args.W[h], d, 1, m0, n0, B, d, args.D[h]);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= B) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < d) dz[(size_t)m * d + n] = acc[i][j];
+    }
+  }
+}
+
+// dW[h][m][n] = sum_k gout[h][k][m] z[k][n]  (m over D[h], n over d, k over B); db[h][m] = sum_k gout[h][k][m]
+__global__ void __launch_bounds__(256)
+    heads_bwd_dw_kernel(const float* __restrict__ z, int B, int d, const __grid_constant__ HeadsArgs args) {
+  __shared__ TileSmem sm;
+  const int h = blockIdx.z, D = args.D[h];
+  const int n0 = blockIdx.x * kTN, m0 = blockIdx.y * kTM;
+  if (m0 >= D) return;
+  float acc[4][4];
+  zero_acc(acc);
+  tile_gemm_accum(sm, acc, args.gout[h], 1, D, z, d, 1, m0, n0, D, d, B);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= D) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < d) args.dW[h][(size_t)m * d + n] = acc[i][j];
+    }
+  }
+  if (blockIdx.x == 0 && args.db[h]) {   // bias gradient: column sums of gout[h], fixed order
+    for (int m = m0 + threadIdx.x; m < D && m < m0 + kTM; m += 256) {
+      float s = 0.f;
+      for (int k = 0; k < B; ++k) s += args.gout[h][(size_t)k * D + m];
+      args.db[h][m] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- Gaussian (A7) ------
+struct GaussArgs {
+  // modality m is the concatenation (like torch.cat(dim=-1)) of n_seg[m] segments
+  const float* val[kMaxMods][kMaxSegs];
+  const float* msk[kMaxMods][kMaxSegs];
+  int F[kMaxMods][kMaxSegs];
+  int n_seg[kMaxMods];
+  const float* mu[kMaxMods];
+  const float* sigma[kMaxMods];
+  float* dmu[kMaxMods];
+  float* dsigma[kMaxMods];
+  int D[kMaxMods];
+  int n_mod;
+};
+
+// One CTA per (utterance b, modality m).  Thread f walks the T time steps of feature f:
+//   S0 = sum m, S1 = sum m (x - mu), S2 = sum m (x - mu)^2          (coalesced across f)
+//   lp_f = -0.5 log(2 pi sigma^2) S0 - S2 / (2 sigma^2)
+//   d lp/d mu = S1 / sigma^2,   d lp/d sigma = -S0 / sigma + S2 / sigma^3
+__global__ void __launch_bounds__(128)
+    gauss_ll_kernel(const __grid_constant__ GaussArgs args, int B, int T, float* __restrict__ lp,
+                    int* __restrict__ status) {
+  __shared__ float red[4];
+  const int b = blockIdx.x, m = blockIdx.y;
+  const int D = args.D[m];
+  float lp_acc = 0.f;
+  for (int f = threadIdx.x; f < D; f += blockDim.x) {
+    int seg = 0, fl = f;
+    while (seg + 1 < args.n_seg[m] && fl >= args.F[m][seg]) { fl -= args.F[m][seg]; ++seg; }
+    const int F = args.F[m][seg];
+    const float* x = args.val[m][seg] + (size_t)b * T * F + fl;
+    const float* k = args.msk[m][seg] + (size_t)b * T * F + fl;
+    const float mu = __ldg(args.mu[m] + (size_t)b * D + f);
+    const float sg = __ldg(args.sigma[m] + (size_t)b * D + f);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float mk = __ldg(k + (size_t)t * F);
+      const float df = __ldg(x + (size_t)t * F) - mu;
+      s0 += mk;
+      s1 = fmaf(mk, df, s1);
+      s2 = fmaf(mk * df, df, s2);
+    }
+    const float var = sg * sg;
+    const float inv_var = 1.f / var;
+    lp_acc += -0.5f * logf(6.283185307179586f * var) * s0 - 0.5f * s2 * inv_var;
+    if (args.dmu[m]) args.dmu[m][(size_t)b * D + f] = s1 * inv_var;
+    if (args.dsigma[m]) args.dsigma[m][(size_t)b * D + f] = (s2 * inv_var - s0) / sg;
+  }
+  lp_acc = warp_sum(lp_acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lp_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float s = red[0] + red[1] + red[2] + red[3];
+    lp[(size_t)m * B + b] = s;
+    if (!isfinite(s)) atomicOr(status, MMB_STATUS_NONFINITE);
+  }
+}
+
+// ---------------------------------------------------------------- word term (A8) -----
+__global__ void row_inv_norm_kernel(const float* __restrict__ X, int64_t n, int d, float* __restrict__ out) {
+  // one warp per row: 1 / max(||x||, 1e-8)   (torch CosineSimilarity eps)
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  float s = 0.f;
+  for (int k = lane; k < d; k += 32) {
+    const float v = __ldg(X + row * d + k);
+    s = fmaf(v, v, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[row] = 1.f / fmaxf(sqrtf(s), 1e-8f);
+}
+
+constexpr float kInvPi = 0.3183098861837907f;
+
+// C tile = (e . w_v) * ie_b * iw_v;  writes S[b][v] = 1 - acos(c)/pi and
+// Hc[b][v] = h(c) * iw_v with h(c) = 1 / (pi sqrt(1 - c^2)), Q[b][v] = h(c) * c.
+__global__ void __launch_bounds__(256)
+    word_cos_kernel(const float* __restrict__ e, const float* __restrict__ ie, int B, int d,
+                    const float* __restrict__ W, const float* __restrict__ iw, int V, float* __restrict__ S,
+                    float* __restrict__ Hw, float* __restrict__ Q) {
+  __shared__ TileSmem sm;
+  const int n0 = blockIdx.x * kTN, m0 = blockIdx.y * kTM;
+  float acc[4][4];
+  zero_acc(acc);
+  tile_gemm_accum(sm, acc, e, d, 1, W, 1, d, m0, n0, B, V, d);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= B) continue;
+    const float iem = ie[m];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= V) continue;
+      const float iwn = iw[n];
+      const float c = acc[i][j] * iem * iwn;
+      const float h = kInvPi / sqrtf(1.f - c * c);
+      S[(size_t)m * V + n] = 1.f - acosf(c) * kInvPi;
+      Hw[(size_t)m * V + n] = h * iwn;
+      Q[(size_t)m * V + n] = h * c;
+    }
+  }
+}
+
+// Hsum[b][:] = sum_v Hw[b][v] * W[v][:]   ((B x V) x (V x d))
+__global__ void __launch_bounds__(256)
+    word_h_kernel(const float* __restrict__ Hw, const float* __restrict__ W, int B, int V, int d,
+                  float* __restrict__ Hsum) {
+  __shared__ TileSmem sm;
+  const int n0 = blockIdx.x * kTN, m0 = blockIdx.y * kTM;
+  float acc[4][4];
+  zero_acc(acc);
+  tile_gemm_accum(sm, acc, Hw, V, 1, W, d, 1, m0, n0, B, d, V);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= B) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < d) Hsum[(size_t)m * d + n] = acc[i][j];
+    }
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+  return s;
+}
+
+// One CTA (256 threads) per utterance: partition sum, per-token terms, lp and d lp / d e.
+__global__ void __launch_bounds__(256)
+    word_finish_kernel(const float* __restrict__ e, const float* __restrict__ ie, int B, int d, int V,
+                       const float* __restrict__ S, const float* __restrict__ Q,
+                       const float* __restrict__ Hsum, const float* __restrict__ sent, int64_t s_sb,
+                       int64_t s_st, const float* __restrict__ word_w, const float* __restrict__ tmask,
+                       int64_t m_sb, int64_t m_st, int L, float a, float* __restrict__ lp,
+                       float* __restrict__ grad, int* __restrict__ status) {
+  extern __shared__ float dyn[];   // L floats: r_t, then L floats: c_t
+  __shared__ float red[8];
+  __shared__ float bc[4];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* r_t = dyn;
+  float* c_t = dyn + L;
+  // Z = sum_v S, hc = sum_v Q   (fixed order per thread, then block tree)
+  float z = 0.f, hc = 0.f;
+  for (int v = tid; v < V; v += 256) {
+    z += S[(size_t)b * V + v];
+    hc += Q[(size_t)b * V + v];
+  }
+  const float Z = block_sum(z, red);
+  const float HC = block_sum(hc, red);
+  const float inv_e = ie[b];
+  const float alpha = 1.f / (Z * a + 1.f);
+  // per-token cosine: one warp per token
+  for (int t = warp; t < L; t += 8) {
+    const float* s = sent + (size_t)b * s_sb + (size_t)t * s_st;
+    float dot = 0.f, nn = 0.f;
+    for (int k = lane; k < d; k += 32) {
+      const float sv = __ldg(s + k);
+      dot = fmaf(sv, __ldg(e + (size_t)b * d + k), dot);
+      nn = fmaf(sv, sv, nn);
+    }
+    dot = warp_sum(dot);
+    nn = warp_sum(nn);
+    if (lane == 0) {
+      const float is = 1.f / fmaxf(sqrtf(nn), 1e-8f);
+      c_t[t] = dot * inv_e * is;
+      r_t[t] = is;   // temporarily the token's inverse norm
+    }
+  }
+  __syncthreads();
+  float lp_acc = 0.f, dz_acc = 0.f, rc_acc = 0.f;
+  for (int t = tid; t < L; t += 256) {
+    const float c = c_t[t], is = r_t[t];
+    const float st = 1.f - acosf(c) * kInvPi;
+    const float w = word_w[(size_t)b * L + t];
+    const float mk = tmask[(size_t)b * m_sb + (size_t)t * m_st];
+    const float p = alpha * w + (1.f - alpha) * st / Z;
+    lp_acc += logf(p) * mk;
+    const float dlp_dp = mk / p;
+    const float dp_dZ = (-a * alpha * alpha) * (w - st / Z) - (1.f - alpha) * st / (Z * Z);
+    dz_acc += dlp_dp * dp_dZ;
+    const float rr = dlp_dp * (1.f - alpha) / Z * (kInvPi / sqrtf(1.f - c * c));
+    rc_acc += rr * c;
+    r_t[t] = rr * is;       // weight of the raw token vector in the gradient
+  }
+  const float LP = block_sum(lp_acc, red);
+  const float DZ = block_sum(dz_acc, red);
+  const float RC = block_sum(rc_acc, red);
+  if (tid == 0) {
+    lp[b] = LP;
+    if (!isfinite(LP)) atomicOr(status, MMB_STATUS_NONFINITE);
+    bc[0] = DZ;
+  }
+  __syncthreads();
+  // d lp/d e = [ DZ * (Hsum - HC * ehat) + sum_t r_t shat_t - RC * ehat ] / ||e||
+  for (int k = tid; k < d; k += 256) {
+    const float eh = e[(size_t)b * d + k] * inv_e;
+    float g = DZ * (Hsum[(size_t)b * d + k] - HC * eh) - RC * eh;
+    float tok = 0.f;
+    for (int t = 0; t < L; ++t) tok = fmaf(r_t[t], __ldg(sent + (size_t)b * s_sb + (size_t)t * s_st + k), tok);
+    grad[(size_t)b * d + k] = (g + tok) * inv_e;
+  }
+}
+
+}  // namespace mmb
 
 using namespace mmb;
 
-#define MMB_TODO(name)                               \
-  do {                                               \
-    set_error(name ": not implemented in this build"); \
-    return MMB_E_UNSUPPORTED;                        \
-  } while (0)
+extern "C" int mmb_heads_forward(const float* z, int B, int d, int n_heads, const float* const* W,
+                                 const float* const* b, const int* D, const int* is_log_sigma,
+                                 float* const* out, mmb_stream_t stream) {
+  MMB_REQUIRE(z && W && b && D && is_log_sigma && out, "null pointer");
+  MMB_REQUIRE(n_heads > 0 && n_heads <= kMaxHeads, "1..16 heads");
+  MMB_REQUIRE(B > 0 && d > 0, "bad size");
+  HeadsArgs a = {};
+  int max_D = 0;
+  for (int h = 0; h < n_heads; ++h) {
+    MMB_REQUIRE(W[h] && b[h] && out[h] && D[h] > 0, "null head");
+    a.W[h] = W[h]; a.b[h] = b[h]; a.out[h] = out[h]; a.D[h] = D[h]; a.is_ls[h] = is_log_sigma[h];
+    if (D[h] > max_D) max_D = D[h];
+  }
+  a.n_heads = n_heads;
+  dim3 grid((max_D + kTN - 1) / kTN, (B + kTM - 1) / kTM, n_heads);
+  heads_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(z, B, d, a);
+  MMB_LAUNCH_CHECK("heads_fwd");
+  return MMB_OK;
+}
 
-extern "C" int mmb_heads_forward(const float*, int, int, int, const float* const*, const float* const*,
-                                 const int*, const int*, float* const*, int, mmb_stream_t) {
-  MMB_TODO("mmb_heads_forward");
+extern "C" int mmb_heads_backward(const float* z, int B, int d, int n_heads, const float* const* W,
+                                  const int* D, const float* const* gout, float* dz, float* const* dW,
+                                  float* const* db, mmb_stream_t stream) {
+  MMB_REQUIRE(z && W && D && gout, "null pointer");
+  MMB_REQUIRE(n_heads > 0 && n_heads <= kMaxHeads, "1..16 heads");
+  MMB_REQUIRE(B > 0 && d > 0, "bad size");
+  HeadsArgs a = {};
+  int max_D = 0;
+  for (int h = 0; h < n_heads; ++h) {
+    MMB_REQUIRE(W[h] && gout[h] && D[h] > 0, "null head");
+    a.W[h] = W[h]; a.gout[h] = gout[h]; a.D[h] = D[h];
+    a.dW[h] = dW ? dW[h] : nullptr;
+    a.db[h] = db ? db[h] : nullptr;
+    if (D[h] > max_D) max_D = D[h];
+  }
+  a.n_heads = n_heads;
+  cudaStream_t st = as_stream(stream);
+  if (dz) {
+    dim3 grid((d + kTN - 1) / kTN, (B + kTM - 1) / kTM);
+    heads_bwd_dz_kernel<<<grid, 256, 0, st>>>(dz, B, d, a);
+    MMB_LAUNCH_CHECK("heads_bwd_dz");
+  }
+  if (dW) {
+    for (int h = 0; h < n_heads; ++h) MMB_REQUIRE(dW[h], "null dW");
+    dim3 grid((d + kTN - 1) / kTN, (max_D + kTM - 1) / kTM, n_heads);
+    heads_bwd_dw_kernel<<<grid, 256, 0, st>>>(z, B, d, a);
+    MMB_LAUNCH_CHECK("heads_bwd_dw");
+  }
+  return MMB_OK;
 }
-extern "C" int mmb_gauss_ll(const float* const*, const float* const*, const int*, int, int, int, const int*,
-                            const float* const*, const float* const*, float*, float* const*, float* const*,
-                            int*, mmb_stream_t) {
-  MMB_TODO("mmb_gauss_ll");
+
+extern "C" int mmb_gauss_ll(int B, int T, int n_mod, const int* n_seg, const float* const* seg_val,
+                            const float* const* seg_mask, const int* seg_F, const float* const* mu,
+                            const float* const* sigma, float* lp, float* const* dmu, float* const* dsigma,
+                            int* status, mmb_stream_t stream) {
+  MMB_REQUIRE(n_seg && seg_val && seg_mask && seg_F && mu && sigma && lp && status, "null pointer");
+  MMB_REQUIRE(n_mod > 0 && n_mod <= kMaxMods, "1..8 modalities");
+  MMB_REQUIRE(B > 0 && T > 0, "bad size");
+  GaussArgs a = {};
+  int s = 0;
+  for (int m = 0; m < n_mod; ++m) {
+    MMB_REQUIRE(n_seg[m] > 0 && n_seg[m] <= kMaxSegs, "1..4 segments per modality");
+    a.n_seg[m] = n_seg[m];
+    int D = 0;
+    for (int g = 0; g < n_seg[m]; ++g, ++s) {
+      MMB_REQUIRE(seg_val[s] && seg_mask[s] && seg_F[s] > 0, "null segment");
+      a.val[m][g] = seg_val[s]; a.msk[m][g] = seg_mask[s]; a.F[m][g] = seg_F[s];
+      D += seg_F[s];
+    }
+    MMB_REQUIRE(mu[m] && sigma[m], "null mu/sigma");
+    a.mu[m] = mu[m]; a.sigma[m] = sigma[m]; a.D[m] = D;
+    a.dmu[m] = dmu ? dmu[m] : nullptr;
+    a.dsigma[m] = dsigma ? dsigma[m] : nullptr;
+  }
+  a.n_mod = n_mod;
+  gauss_ll_kernel<<<dim3(B, n_mod), 128, 0, as_stream(stream)>>>(a, B, T, lp, status);
+  MMB_LAUNCH_CHECK("gauss_ll");
+  return MMB_OK;
 }
-extern "C" int mmb_row_inv_norm(const float*, int64_t, int, float*, mmb_stream_t) {
-  MMB_TODO("mmb_row_inv_norm");
+
+extern "C" int mmb_row_inv_norm(const float* X, int64_t n, int d, float* inv_norm, mmb_stream_t stream) {
+  MMB_REQUIRE(X && inv_norm, "null pointer");
+  MMB_REQUIRE(n >= 0 && d > 0, "bad size");
+  if (n == 0) return MMB_OK;
+  row_inv_norm_kernel<<<(unsigned)((n + 7) / 8), 256, 0, as_stream(stream)>>>(X, n, d, inv_norm);
+  MMB_LAUNCH_CHECK("row_inv_norm");
+  return MMB_OK;
 }
-extern "C" size_t mmb_word_ll_workspace_bytes(int, int64_t, int) { return 0; }
-extern "C" int mmb_word_ll(const float*, int, int, const float*, const float*, int64_t, const float*, int64_t,
-                           int64_t, const float*, const float*, int64_t, int64_t, int, float, float*, float*,
-                           void*, size_t, int*, mmb_stream_t) {
-  MMB_TODO("mmb_word_ll");
+
+extern "C" size_t mmb_word_ll_workspace_bytes(int B, int64_t V, int d) {
+  // S, Hw, Q: (B, V) each; Hsum: (B, d); ie: (B)
+  return ((size_t)3 * B * V + (size_t)B * d + B) * sizeof(float) + 256;
+}
+
+extern "C" int mmb_word_ll(const float* latents, int B, int d, const float* table, const float* inv_norm,
+                           int64_t V, const float* sent, int64_t sent_stride_b, int64_t sent_stride_t,
+                           const float* word_w, const float* tmask, int64_t tmask_stride_b,
+                           int64_t tmask_stride_t, int L, float a, float* lp, float* grad, void* ws,
+                           size_t ws_bytes, int* status, mmb_stream_t stream) {
+  MMB_REQUIRE(latents && table && inv_norm && sent && word_w && tmask && lp && grad && ws && status,
+              "null pointer");
+  MMB_REQUIRE(B > 0 && d > 0 && V > 0 && L > 0 && V < (1 << 30), "bad size");
+  MMB_REQUIRE(ws_bytes >= mmb_word_ll_workspace_bytes(B, V, d), "workspace too small");
+  MMB_REQUIRE((size_t)2 * L * sizeof(float) <= 48 * 1024, "L too large for the per-utterance kernel");
+  cudaStream_t st = as_stream(stream);
+  float* S = (float*)ws;
+  float* Hw = S + (size_t)B * V;
+  float* Q = Hw + (size_t)B * V;
+  float* Hsum = Q + (size_t)B * V;
+  float* ie = Hsum + (size_t)B * d;
+  row_inv_norm_kernel<<<(B + 7) / 8, 256, 0, st>>>(latents, B, d, ie);
+  MMB_LAUNCH_CHECK("row_inv_norm(latents)");
+  dim3 g1((unsigned)((V + kTN - 1) / kTN), (B + kTM - 1) / kTM);
+  word_cos_kernel<<<g1, 256, 0, st>>>(latents, ie, B, d, table, inv_norm, (int)V, S, Hw, Q);
+  MMB_LAUNCH_CHECK("word_cos");
+  dim3 g2((d + kTN - 1) / kTN, (B + kTM - 1) / kTM);
+  word_h_kernel<<<g2, 256, 0, st>>>(Hw, table, B, (int)V, d, Hsum);
+  MMB_LAUNCH_CHECK("word_h");
+  word_finish_kernel<<<B, 256, 2 * L * sizeof(float), st>>>(latents, ie, B, d, (int)V, S, Q, Hsum, sent,
+                                                          sent_stride_b, sent_stride_t, word_w, tmask,
+                                                          tmask_stride_b, tmask_stride_t, L, a, lp, grad, status);
+  MMB_LAUNCH_CHECK("word_finish");
+  return MMB_OK;
 }

@@ -46,24 +46,34 @@ __device__ void small_gram(PcSmem& sm, const double* A, const double* B, int d, 
   __syncthreads();
 }
 
-// In-place upper Cholesky S = R^T R by thread 0; columns whose pivot is not positive relative
-// to the largest diagonal entry are dropped (they lie in the span of earlier columns).
+// In-place upper Cholesky S = R^T R (right-looking, warp 0, lane j owns column j); columns
+// whose pivot is not positive relative to the largest diagonal entry are dropped (they lie in
+// the span of earlier columns).  sm.lam[c] receives 1 / R[c][c] for apply_rinv.
 __device__ void cholesky_drop(PcSmem& sm, int k) {
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    const int j = threadIdx.x;
     double dmax = 0.0;
     for (int c = 0; c < k; ++c) dmax = fmax(dmax, sm.S[c][c]);
     for (int c = 0; c < k; ++c) {
-      for (int a = 0; a <= c; ++a) {
-        double s = sm.S[a][c];
-        for (int b = 0; b < a; ++b) s -= sm.S[b][a] * sm.S[b][c];
-        if (a < c) {
-          sm.S[a][c] = sm.drop[a] ? 0.0 : s / sm.S[a][a];
-        } else {
-          const bool bad = !(s > 1e-26 * dmax) || !isfinite(s);
-          sm.drop[c] = bad;
-          sm.S[c][c] = bad ? 1.0 : sqrt(s);
-        }
+      const double piv = sm.S[c][c];
+      const bool bad = !(piv > 1e-26 * dmax) || !isfinite(piv);
+      const double rinv = bad ? 0.0 : rsqrt(piv);
+      __syncwarp();
+      if (j == c) {
+        sm.drop[c] = bad;
+        sm.S[c][c] = bad ? 1.0 : piv * rinv;   // sqrt(piv)
+        sm.lam[c] = bad ? 0.0 : rinv;
       }
+      double rcj = 0.0;
+      if (j > c && j < k) {
+        rcj = sm.S[c][j] * rinv;               // row c of R (0 for a dropped column)
+        sm.S[c][j] = rcj;
+      }
+      __syncwarp();
+      if (j > c && j < k) {                    // trailing update of column j, rows c+1..j
+        for (int i = c + 1; i <= j; ++i) sm.S[i][j] -= sm.S[c][i] * rcj;
+      }
+      __syncwarp();
     }
   }
   __syncthreads();
@@ -79,7 +89,7 @@ __device__ void apply_rinv(const PcSmem& sm, double (&q)[KMAX], int k) {
 #pragma unroll
       for (int a = 0; a < KMAX; ++a)
         if (a < c) acc -= q[a] * sm.S[a][c];
-      q[c] = sm.drop[c] ? 0.0 : acc / sm.S[c][c];
+      q[c] = acc * sm.lam[c];   // lam[c] = 1 / R[c][c], 0 for a dropped column
     }
   }
 }
@@ -97,8 +107,8 @@ __device__ void store_row(double* M, const double (&q)[KMAX], int row, int d, in
 // CholeskyQR2 on the rows held in registers; Qg (global, d x k) is scratch and ends up
 // holding the orthonormalised block.
 template <int KMAX>
-__device__ void orth(PcSmem& sm, double (&q)[KMAX], double* Qg, int row, int d, int k) {
-  for (int pass = 0; pass < 2; ++pass) {
+__device__ void orth(PcSmem& sm, double (&q)[KMAX], double* Qg, int row, int d, int k, int passes) {
+  for (int pass = 0; pass < passes; ++pass) {
     store_row<KMAX>(Qg, q, row, d, k);
     small_gram(sm, Qg, Qg, d, k, true);
     cholesky_drop(sm, k);
@@ -132,7 +142,7 @@ __device__ void jacobi_eig(PcSmem& sm, int k) {
     for (int c = 0; c < k; ++c)
       if (l < k) sm.Vv[l][c] = (l == c) ? 1.0 : 0.0;
     __syncwarp();
-    for (int sweep = 0; sweep < 40; ++sweep) {
+    for (int sweep = 0; sweep < 16; ++sweep) {
       double off = 0.0, dg = 0.0;
       if (l < k) {
         for (int c = 0; c < k; ++c) {
@@ -143,11 +153,11 @@ __device__ void jacobi_eig(PcSmem& sm, int k) {
       }
       off = warp_sum(off);
       dg = warp_sum(dg);
-      if (!(off > 1e-32 * dg)) break;
+      if (!(off > 1e-27 * dg)) break;   // off-diagonal mass below ~3e-14 of the diagonal: converged
       for (int p = 0; p < k - 1; ++p) {
         for (int q = p + 1; q < k; ++q) {
           const double apq = sm.S[p][q];
-          if (fabs(apq) > 1e-300) {
+          if (fabs(apq) > 1e-17 * sqrt(fabs(sm.S[p][p] * sm.S[q][q])) && fabs(apq) > 1e-300) {
             const double app = sm.S[p][p], aqq = sm.S[q][q];
             const double theta = (aqq - app) / (2.0 * apq);
             const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
@@ -207,13 +217,15 @@ __global__ void __launch_bounds__(512)
   if (threadIdx.x < kPcMaxK) sm.drop[threadIdx.x] = 0;
   __syncthreads();
 
-  orth<KMAX>(sm, q, Qg, row, d, k);
+  // Only the span matters between multiplications, so one CholeskyQR pass keeps the block
+  // well enough conditioned there; the last one is repeated (CholeskyQR2) for orthonormality.
+  orth<KMAX>(sm, q, Qg, row, d, k, n_iter == 0 ? 2 : 1);
   for (int it = 0; it < n_iter; ++it) {
     gram_times<KMAX>(G, Qg, y, row, d, k);
     __syncthreads();  // everyone has finished reading Qg
 #pragma unroll
     for (int c = 0; c < KMAX; ++c) q[c] = y[c];
-    orth<KMAX>(sm, q, Qg, row, d, k);
+    orth<KMAX>(sm, q, Qg, row, d, k, it + 1 == n_iter ? 2 : 1);
   }
   gram_times<KMAX>(G, Qg, y, row, d, k);
   store_row<KMAX>(Yg, y, row, d, k);

@@ -46,38 +46,80 @@ __global__ void __launch_bounds__(256) seq2weight_kernel(const int64_t* __restri
   if (bad) atomicOr(status, MMB_STATUS_BAD_INDEX);
 }
 
-// One token's contribution: acc[c] += wj * row[lane + 32 c].
+// Packed FP32 pairs: Blackwell issues two FP32 FMAs per lane per instruction (fma.rn.f32x2,
+// SASS FFMA2), which halves the FMA issue slots of this issue-bound kernel.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(f32x2& acc, f32x2 a, f32x2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
 template <int NCH>
-__device__ __forceinline__ void load_row(float4 (&v)[NCH], const float4* __restrict__ p, int lane,
-                                         int d4) {
+struct RowAcc {
+  f32x2 a[NCH][2];
+  __device__ __forceinline__ void clear() {
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    int k = lane + 32 * c;
-    v[c] = ((NCH <= 4 && c + 1 < NCH) || k < d4) ? __ldg(p + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < NCH; ++c) a[c][0] = a[c][1] = 0ull;   // bit pattern of (0.f, 0.f)
   }
+};
+
+// One gathered row: v[c] = row[lane + 32 c] (coalesced 16-byte loads through the read-only path).
+// `tail` = this lane takes part in the last, partial chunk (d4 not a multiple of 32); the other
+// lanes neither load nor accumulate that chunk.
+template <int NCH>
+__device__ __forceinline__ void load_row(float4 (&v)[NCH], const char* __restrict__ lane_base, size_t off,
+                                         bool tail) {
+  const float4* p = (const float4*)(lane_base + off);
+#pragma unroll
+  for (int c = 0; c + 1 < NCH; ++c) v[c] = __ldg(p + 32 * c);
+  if (tail) v[NCH - 1] = __ldg(p + 32 * (NCH - 1));
 }
 template <int NCH>
-__device__ __forceinline__ void fma_row(float4 (&acc)[NCH], const float4 (&v)[NCH], float w) {
+__device__ __forceinline__ void fma_row(RowAcc<NCH>& acc, const float4 (&v)[NCH], float w, bool tail) {
+  const f32x2 ww = pack2(w, w);
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    acc[c].x = fmaf(w, v[c].x, acc[c].x);
-    acc[c].y = fmaf(w, v[c].y, acc[c].y);
-    acc[c].z = fmaf(w, v[c].z, acc[c].z);
-    acc[c].w = fmaf(w, v[c].w, acc[c].w);
+  for (int c = 0; c + 1 < NCH; ++c) {
+    ffma2(acc.a[c][0], ww, pack2(v[c].x, v[c].y));
+    ffma2(acc.a[c][1], ww, pack2(v[c].z, v[c].w));
+  }
+  if (tail) {
+    ffma2(acc.a[NCH - 1][0], ww, pack2(v[NCH - 1].x, v[NCH - 1].y));
+    ffma2(acc.a[NCH - 1][1], ww, pack2(v[NCH - 1].z, v[NCH - 1].w));
   }
 }
 
+// Byte offset of a table row: 32-bit when the whole table is < 4 GiB (one IMAD per token-lane,
+// computed in parallel by the 32 lanes and then shuffled), 64-bit otherwise.
+template <bool WIDE> struct RowOff;
+template <> struct RowOff<false> { typedef unsigned type; };
+template <> struct RowOff<true> { typedef unsigned long long type; };
+
 // Accumulate tokens [base, base+32) of utterance i (lane = token) into acc; returns the
 // number of non-zero weights among them.
-template <int NCH, bool EXPLICIT_W>
-__device__ __forceinline__ int accumulate_chunk(float4 (&acc)[NCH], const float4* __restrict__ table4,
-                                                int V, int d4, const float* __restrict__ wsrc,
+//
+// Runs of equal adjacent ids are merged first: sum_j w_j * row == (sum_j w_j) * row, so a run
+// costs one row read instead of its length.  Right-padded batches end in a long run of the pad
+// id (37 % of the tokens of the bench workload, 73 % of the POM fixtures), which the reference
+// dutifully gathers and adds one by one (pad id 0 is an ordinary row with weight 1.0 in the POM
+// weights).  The divisor still counts every token's own weight.
+template <int NCH, bool EXPLICIT_W, int UNROLL, bool WIDE>
+__device__ __forceinline__ int accumulate_chunk(RowAcc<NCH>& acc, const char* __restrict__ lane_base,
+                                                int V, unsigned row_bytes, bool tail,
+                                                const float* __restrict__ wsrc,
                                                 const int64_t* __restrict__ row_ids,
                                                 const float* __restrict__ row_w, int64_t base,
                                                 int64_t L, int lane, bool& bad) {
+  typedef typename RowOff<WIDE>::type off_t;
   const int64_t t = base + lane;
   float w = 0.f;
-  int row = 0;
+  int row = -1;                       // -1: no token in this lane (past the end / bad index)
   if (t < L) {
     const int64_t id = __ldcs(row_ids + t);
     const int64_t r = id < 0 ? id + V : id;
@@ -88,41 +130,85 @@ __device__ __forceinline__ int accumulate_chunk(float4 (&acc)[NCH], const float4
       bad = true;  // NumPy: IndexError
     }
   }
+  const off_t off = (off_t)(row < 0 ? 0 : row) * row_bytes;
   const int cnt = __popc(__ballot_sync(0xffffffffu, w != 0.f));
-  const int n_tok = (int)((L - base) < 32 ? (L - base) : 32);
-  int j = 0;
-  // 4 tokens per trip: 4 x NCH independent 16-byte loads in flight per lane before the FMAs.
-  for (; j + 4 <= n_tok; j += 4) {
-    float wj[4];
-    float4 v[4][NCH];
+  // run heads: first lane of every maximal run of equal rows
+  const int prev = __shfl_up_sync(0xffffffffu, row, 1);
+  const bool head = (row >= 0) && (lane == 0 || row != prev);
+  const unsigned valid = __ballot_sync(0xffffffffu, row >= 0);
+  unsigned heads = __ballot_sync(0xffffffffu, head);
+  if (heads == 0xffffffffu) {
+    // common case (32 distinct neighbours): fixed shuffle lanes, no bit scanning
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      wj[u] = __shfl_sync(0xffffffffu, w, j + u);
-      const int rj = __shfl_sync(0xffffffffu, row, j + u);
-      load_row<NCH>(v[u], table4 + (size_t)rj * d4, lane, d4);
+    for (int j0 = 0; j0 < 32; j0 += UNROLL) {
+      float wj[UNROLL];
+      float4 v[UNROLL][NCH];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        wj[u] = __shfl_sync(0xffffffffu, w, j0 + u);
+        const off_t oj = __shfl_sync(0xffffffffu, off, j0 + u);
+        load_row<NCH>(v[u], lane_base, oj, tail);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) fma_row<NCH>(acc, v[u], wj[u], tail);
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) fma_row<NCH>(acc, v[u], wj[u]);
+    return cnt;
   }
-  for (; j < n_tok; ++j) {
-    const float wj = __shfl_sync(0xffffffffu, w, j);
-    const int rj = __shfl_sync(0xffffffffu, row, j);
-    float4 v[NCH];
-    load_row<NCH>(v, table4 + (size_t)rj * d4, lane, d4);
-    fma_row<NCH>(acc, v, wj);
+  if (heads != valid) {
+    // segmented sum of the weights of each run into its head lane; a run ends where the next
+    // run (or an empty lane) starts
+    const unsigned breaks = (heads | ~valid) & ~((2u << lane) - 1u);   // run starts / gaps above me
+    const int run_end = breaks ? (__ffs(breaks) - 2) : 31;   // last lane of my run
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float up = __shfl_down_sync(0xffffffffu, w, o);
+      if (lane + o <= run_end) w += up;
+    }
+  }
+  // walk the heads, UNROLL rows in flight per lane
+  while (heads) {
+    int j[UNROLL];
+    int n = 0;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      j[u] = heads ? (__ffs(heads) - 1) : 0;
+      if (heads) { heads &= heads - 1; ++n; }
+    }
+    if (n == UNROLL) {
+      float wj[UNROLL];
+      float4 v[UNROLL][NCH];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        wj[u] = __shfl_sync(0xffffffffu, w, j[u]);
+        const off_t oj = __shfl_sync(0xffffffffu, off, j[u]);
+        load_row<NCH>(v[u], lane_base, oj, tail);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) fma_row<NCH>(acc, v[u], wj[u], tail);
+    } else {
+      for (int u = 0; u < n; ++u) {
+        const float wu = __shfl_sync(0xffffffffu, w, j[u]);
+        const off_t oj = __shfl_sync(0xffffffffu, off, j[u]);
+        float4 vv[NCH];
+        load_row<NCH>(vv, lane_base, oj, tail);
+        fma_row<NCH>(acc, vv, wu, tail);
+      }
+    }
   }
   return cnt;
 }
 
 template <int NCH>
-__device__ __forceinline__ void store_row(float4* __restrict__ out, const float4 (&acc)[NCH],
-                                          int cnt, int lane, int d4) {
+__device__ __forceinline__ void store_row(float4* __restrict__ out, const RowAcc<NCH>& acc, int cnt,
+                                          int lane, int d4) {
   const float div = (float)cnt;  // 0 -> inf/NaN row, as NumPy's true_divide
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     int k = lane + 32 * c;
     if ((NCH <= 4 && c + 1 < NCH) || k < d4) {
-      float4 r = acc[c];
+      float4 r;
+      unpack2(acc.a[c][0], r.x, r.y);
+      unpack2(acc.a[c][1], r.z, r.w);
       r.x = __fdiv_rn(r.x, div);
       r.y = __fdiv_rn(r.y, div);
       r.z = __fdiv_rn(r.z, div);
@@ -133,8 +219,8 @@ __device__ __forceinline__ void store_row(float4* __restrict__ out, const float4
 }
 
 // Warp-per-utterance variant (large N).
-template <int NCH, bool EXPLICIT_W>
-__global__ void __launch_bounds__(kEmbedWarps * 32)
+template <int NCH, bool EXPLICIT_W, int UNROLL, int MINB, bool WIDE>
+__global__ void __launch_bounds__(kEmbedWarps * 32, MINB)
     sif_embed_warp_kernel(const float4* __restrict__ table4, int V, int d4,
                           const float* __restrict__ wsrc, const int64_t* __restrict__ ids,
                           int64_t N, int64_t L, float4* __restrict__ emb4,
@@ -142,17 +228,19 @@ __global__ void __launch_bounds__(kEmbedWarps * 32)
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kEmbedWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kEmbedWarps;
+  const char* lane_base = (const char*)(table4 + lane);
+  const unsigned row_bytes = (unsigned)d4 * 16u;
+  const bool tail = lane + 32 * (NCH - 1) < d4;
   bool bad = false;
   for (int64_t i = warp0; i < N; i += nwarps) {
-    float4 acc[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    RowAcc<NCH> acc;
+    acc.clear();
     int cnt = 0;
     const int64_t* row_ids = ids + i * L;
     const float* row_w = EXPLICIT_W ? wsrc + i * L : nullptr;
     for (int64_t base = 0; base < L; base += 32)
-      cnt += accumulate_chunk<NCH, EXPLICIT_W>(acc, table4, V, d4, wsrc, row_ids, row_w, base, L,
-                                               lane, bad);
+      cnt += accumulate_chunk<NCH, EXPLICIT_W, UNROLL, WIDE>(acc, lane_base, V, row_bytes, tail, wsrc, row_ids,
+                                                             row_w, base, L, lane, bad);
     store_row<NCH>(emb4 + (size_t)i * d4, acc, cnt, lane, d4);
   }
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, MMB_STATUS_BAD_INDEX);
@@ -170,19 +258,28 @@ __global__ void __launch_bounds__(kEmbedWarps * 32)
   __shared__ int part_cnt[kEmbedWarps];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const char* lane_base = (const char*)(table4 + lane);
+  const unsigned row_bytes = (unsigned)d4 * 16u;
+  const bool tail = lane + 32 * (NCH - 1) < d4;
   bool bad = false;
   for (int64_t i = blockIdx.x; i < N; i += gridDim.x) {
-    float4 acc[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    RowAcc<NCH> acc;
+    acc.clear();
     int cnt = 0;
     const int64_t* row_ids = ids + i * L;
     const float* row_w = EXPLICIT_W ? wsrc + i * L : nullptr;
     for (int64_t base = 32 * (int64_t)warp; base < L; base += 32 * kEmbedWarps)
-      cnt += accumulate_chunk<NCH, EXPLICIT_W>(acc, table4, V, d4, wsrc, row_ids, row_w, base, L,
-                                               lane, bad);
+      cnt += accumulate_chunk<NCH, EXPLICIT_W, 2, true>(acc, lane_base, V, row_bytes, tail, wsrc, row_ids, row_w,
+                                                        base, L, lane, bad);
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) part[warp][lane + 32 * c] = acc[c];
+    for (int c = 0; c < NCH; ++c) {
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((NCH <= 4 && c + 1 < NCH) || tail) {
+        unpack2(acc.a[c][0], r.x, r.y);
+        unpack2(acc.a[c][1], r.z, r.w);
+      }
+      part[warp][lane + 32 * c] = r;
+    }
     if (lane == 0) part_cnt[warp] = cnt;
     __syncthreads();
     int total = 0;
@@ -220,8 +317,27 @@ static int launch_embed(const float* table, int64_t V, int d, const float* wsrc,
     int64_t blocks = ceil_div(N, kEmbedWarps);
     int64_t cap = (int64_t)sms * 8;
     int grid = (int)(blocks < cap ? blocks : cap);
-    sif_embed_warp_kernel<NCH, EXPLICIT_W><<<grid, kEmbedWarps * 32, 0, st>>>(
-        (const float4*)table, (int)V, d4, wsrc, ids, N, L, (float4*)emb, status);
+    static const int variant = getenv("MMB_EMBED_VARIANT") ? atoi(getenv("MMB_EMBED_VARIANT")) : 0;
+    static const int waves = getenv("MMB_EMBED_WAVES") ? atoi(getenv("MMB_EMBED_WAVES")) : 8;
+    cap = (int64_t)sms * waves;
+    grid = (int)(blocks < cap ? blocks : cap);
+    const bool wide = (uint64_t)V * (uint64_t)d * 4u >= ((uint64_t)1 << 32);
+#define EMBED_LAUNCH(U, B, W)                                                                \
+  sif_embed_warp_kernel<NCH, EXPLICIT_W, U, B, W><<<grid, kEmbedWarps * 32, 0, st>>>(        \
+      (const float4*)table, (int)V, d4, wsrc, ids, N, L, (float4*)emb, status)
+    if (wide) {
+      EMBED_LAUNCH(2, 4, true);
+    } else {
+      switch (variant) {
+        case 1: EMBED_LAUNCH(4, 3, false); break;
+        case 2: EMBED_LAUNCH(2, 5, false); break;
+        case 3: EMBED_LAUNCH(1, 6, false); break;
+        case 4: EMBED_LAUNCH(4, 2, false); break;
+        case 5: EMBED_LAUNCH(2, 3, false); break;
+        default: EMBED_LAUNCH(2, 4, false); break;
+      }
+    }
+#undef EMBED_LAUNCH
   }
   MMB_LAUNCH_CHECK("sif_embed");
   return MMB_OK;

@@ -1,0 +1,174 @@
+"""torch.autograd bindings of the MMB step kernels.
+
+Each Function is one call into libmmb_b200.so that produces the value together with the
+analytic gradients (Appendix A.3-A.5), so ``backward`` is a broadcast multiply (Gaussian,
+word term) or one more library call (heads).  Inputs are made float32 / contiguous CUDA
+tensors; anything else is an error -- there is no CPU fallback.
+"""
+import ctypes as C
+
+import torch
+
+import _native as nv
+from _native import lib
+
+
+def _f32(t):
+    if not t.is_cuda:
+        raise nv.MMBError('libmmb_b200 needs CUDA tensors (got %s); there is no CPU fallback' % t.device)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[0 if t is None else t.data_ptr() for t in tensors])
+
+
+def _int_array(vals):
+    return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+class HeadsFunction(torch.autograd.Function):
+    """All (mu, log_sigma) heads of AudioVisualGeneratorMultimodal in one launch
+    (reference models.py:196-202).  ``apply(z, is_log_sigma, W0, b0, W1, b1, ...)`` returns
+    one (B, D_h) tensor per head; heads flagged in ``is_log_sigma`` get the exp() epilogue."""
+
+    @staticmethod
+    def forward(ctx, z, is_log_sigma, *params):
+        z = _f32(z)
+        Ws = [_f32(p) for p in params[0::2]]
+        bs = [_f32(p) for p in params[1::2]]
+        B, d = z.shape
+        Ds = [w.shape[0] for w in Ws]
+        outs = [torch.empty((B, D), dtype=torch.float32, device=z.device) for D in Ds]
+        nv.check(lib.mmb_heads_forward(nv.ptr(z), B, d, len(Ws), _ptr_array(Ws), _ptr_array(bs),
+                                       _int_array(Ds), _int_array(is_log_sigma), _ptr_array(outs),
+                                       nv.stream_ptr()))
+        ctx.is_log_sigma = list(is_log_sigma)
+        ctx.Ds = Ds
+        ctx.save_for_backward(z, *Ws, *[o for o, ls in zip(outs, is_log_sigma) if ls])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        saved = ctx.saved_tensors
+        n = len(ctx.Ds)
+        z, Ws, sig = saved[0], saved[1:1 + n], list(saved[1 + n:])
+        B, d = z.shape
+        gpre = []
+        for h in range(n):
+            g = gouts[h]
+            g = torch.zeros((B, ctx.Ds[h]), dtype=torch.float32, device=z.device) if g is None else _f32(g)
+            if ctx.is_log_sigma[h]:
+                g = g * sig.pop(0)            # d sigma / d s = sigma  (sigma = exp(s))
+            gpre.append(g.contiguous())
+        need_z = ctx.needs_input_grad[0]
+        need_w = any(ctx.needs_input_grad[2:])
+        dz = torch.empty_like(z) if need_z else None
+        dWs = [torch.empty_like(w) for w in Ws] if need_w else None
+        dbs = [torch.empty(D, dtype=torch.float32, device=z.device) for D in ctx.Ds] if need_w else None
+        nv.check(lib.mmb_heads_backward(nv.ptr(z), B, d, n, _ptr_array(Ws), _int_array(ctx.Ds), _ptr_array(gpre),
+                                        nv.ptr(dz), _ptr_array(dWs) if need_w else None,
+                                        _ptr_array(dbs) if need_w else None, nv.stream_ptr()))
+        grads = [dz, None]
+        for h in range(n):
+            grads.append(dWs[h] if need_w and ctx.needs_input_grad[2 + 2 * h] else None)
+            grads.append(dbs[h] if need_w and ctx.needs_input_grad[3 + 2 * h] else None)
+        return tuple(grads)
+
+
+class GaussLLFunction(torch.autograd.Function):
+    """Masked diagonal-Gaussian log-likelihood of every modality in one launch (reference
+    losses.py:13-34, 251-256).  ``apply(segments, status, mu_0, sigma_0, mu_1, sigma_1, ...)``
+    with ``segments[m]`` = list of (values, mask) pairs whose feature axes concatenate to
+    modality m (the reference's torch.cat, simplesif.py:94-113, without materialising it);
+    returns lp of shape (n_mod, B)."""
+
+    @staticmethod
+    def forward(ctx, segments, status, *mu_sigma):
+        mus = [_f32(t) for t in mu_sigma[0::2]]
+        sigmas = [_f32(t) for t in mu_sigma[1::2]]
+        n_mod = len(mus)
+        B = mus[0].shape[0]
+        vals, masks, Fs, n_seg = [], [], [], []
+        T = None
+        for m in range(n_mod):
+            n_seg.append(len(segments[m]))
+            D = 0
+            for v, k in segments[m]:
+                v, k = _f32(v), _f32(k)
+                if v.dim() != 3 or v.shape != k.shape or v.shape[0] != B:
+                    raise ValueError('values/mask must both be (batch, seq_len, n_features)')
+                T = v.shape[1] if T is None else T
+                if v.shape[1] != T:
+                    raise ValueError('all modalities must share seq_len in one call')
+                vals.append(v)
+                masks.append(k)
+                Fs.append(v.shape[2])
+                D += v.shape[2]
+            if mus[m].shape != (B, D) or sigmas[m].shape != (B, D):
+                raise RuntimeError('The size of mu/sigma %s must match the data (%d, %d)'
+                                   % (tuple(mus[m].shape), B, D))
+        lp = torch.empty((n_mod, B), dtype=torch.float32, device=mus[0].device)
+        dmu = [torch.empty_like(t) for t in mus]
+        dsg = [torch.empty_like(t) for t in sigmas]
+        nv.check(lib.mmb_gauss_ll(B, T, n_mod, _int_array(n_seg), _ptr_array(vals), _ptr_array(masks),
+                                  _int_array(Fs), _ptr_array(mus), _ptr_array(sigmas), nv.ptr(lp),
+                                  _ptr_array(dmu), _ptr_array(dsg), nv.ptr(status), nv.stream_ptr()))
+        ctx.save_for_backward(*dmu, *dsg)
+        ctx.n_mod = n_mod
+        return lp
+
+    @staticmethod
+    def backward(ctx, g):
+        n = ctx.n_mod
+        dmu, dsg = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        grads = [None, None]
+        for m in range(n):
+            gm = g[m].unsqueeze(1)
+            grads.append(gm * dmu[m] if ctx.needs_input_grad[2 + 2 * m] else None)
+            grads.append(gm * dsg[m] if ctx.needs_input_grad[3 + 2 * m] else None)
+        return tuple(grads)
+
+
+class WordLLFunction(torch.autograd.Function):
+    """Angular word log-probability (reference losses.py:68-95) with its gradient w.r.t. the
+    latents; the word table, token vectors, weights and mask are constants of the step."""
+
+    @staticmethod
+    def forward(ctx, latents, table, word_w, sent, mask, a, status):
+        e = _f32(latents)
+        table = _f32(table)
+        word_w = _f32(word_w)
+        sent = sent if (sent.dtype == torch.float32 and sent.is_cuda and sent.stride(-1) == 1) else _f32(sent)
+        if not (mask.dtype == torch.float32 and mask.is_cuda):
+            mask = _f32(mask)
+        B, d = e.shape
+        V = table.shape[0]
+        L = word_w.shape[1]
+        if sent.shape[:2] != (B, L) or sent.shape[2] != d or mask.shape[:2] != (B, L):
+            raise RuntimeError('word term: shapes do not match (latents %s, sent %s, weights %s, mask %s)'
+                               % (tuple(e.shape), tuple(sent.shape), tuple(word_w.shape), tuple(mask.shape)))
+        inv_norm = torch.empty(V, dtype=torch.float32, device=e.device)
+        nv.check(lib.mmb_row_inv_norm(nv.ptr(table), V, d, nv.ptr(inv_norm), nv.stream_ptr()))
+        lp = torch.empty(B, dtype=torch.float32, device=e.device)
+        grad = torch.empty_like(e)
+        nbytes = lib.mmb_word_ll_workspace_bytes(B, V, d)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=e.device)
+        nv.check(lib.mmb_word_ll(nv.ptr(e), B, d, nv.ptr(table), nv.ptr(inv_norm), V,
+                                 C.c_void_p(sent.data_ptr()), sent.stride(0), sent.stride(1),
+                                 nv.ptr(word_w), C.c_void_p(mask.data_ptr()), mask.stride(0), mask.stride(1),
+                                 L, float(a), nv.ptr(lp), nv.ptr(grad), nv.ptr(ws), nbytes, nv.ptr(status),
+                                 nv.stream_ptr()))
+        ctx.save_for_backward(grad)
+        return lp
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return g.unsqueeze(1) * grad, None, None, None, None, None, None
+
+
+def new_status(device):
+    return torch.zeros(1, dtype=torch.int32, device=device)
