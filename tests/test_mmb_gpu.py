@@ -1,0 +1,162 @@
+"""GPU parity of the MMB step (rows A6-A9) through the drop-in modules vs the golden
+fixtures produced by the unmodified reference (values AND autograd gradients)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import mmb_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+VAL_RTOL = 1e-4      # FP32 kernels vs the reference's FP32 torch ops (different summation order)
+GRAD_RTOL = 2e-3     # relative to the largest entry of the gradient tensor
+
+
+@pytest.fixture(scope='module')
+def mods():
+    import torch
+    import losses
+    import models
+    assert torch.cuda.is_available()
+    return torch, losses, models
+
+
+def close(got, want, rtol, name=''):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (name, got.shape, want.shape)
+    scale = max(np.abs(want).max(), 1e-12)
+    err = np.abs(got - want).max() / scale
+    assert err < rtol, (name, err)
+
+
+def build(torch, models, losses, tag, use_segments):
+    cfg = cases.MMB_CASES[tag]
+    c = cases.mmb_inputs(**cfg)
+    dev = torch.device('cuda')
+    model = models.AudioVisualGeneratorMultimodal(c['d'], c['A'], c['Vd'], norm=cfg['norm'],
+                                                  frozen_weights=False, unimodal=cfg['unimodal']).to(dev)
+    cases.load_heads(model, c['heads'], c.get('norm_params'))
+    t = {k: torch.tensor(v, device=dev) for k, v in c.items() if isinstance(v, np.ndarray)}
+    cat = (lambda parts: losses.CatSegments(parts)) if use_segments else (lambda parts: torch.cat(parts, -1))
+    data = {'text': t['text'], 'audio': t['aud'], 'visual': t['vis'], 'text_weights': t['text_w']}
+    masks = {'text': t['text_m'], 'audio': t['aud_m'], 'visual': t['vis_m']}
+    if not cfg['unimodal']:
+        data.update(audiovisual=cat([t['aud'], t['vis']]), textaudio=cat([t['text'], t['aud']]),
+                    textvisual=cat([t['text'], t['vis']]), textaudiovisual=cat([t['text'], t['aud'], t['vis']]))
+        masks.update(audiovisual=cat([t['aud_m'], t['vis_m']]), textaudio=cat([t['text_m'], t['aud_m']]),
+                     textvisual=cat([t['text_m'], t['vis_m']]),
+                     textaudiovisual=cat([t['text_m'], t['aud_m'], t['vis_m']]))
+    return cfg, c, t, model, data, masks
+
+
+def dense(x):
+    return x.materialize() if hasattr(x, 'materialize') else x
+
+
+@pytest.mark.parametrize('tag', list(cases.MMB_CASES))
+@pytest.mark.parametrize('use_segments', [True, False])
+def test_step_matches_reference(mods, golden_dir, tag, use_segments):
+    torch, losses, models = mods
+    g = np.load(os.path.join(golden_dir, 'mmb_%s.npz' % tag))
+    cfg, c, t, model, data, masks = build(torch, models, losses, tag, use_segments)
+    lat = t['latents'].clone().requires_grad_(True)
+    out = model(lat)
+    for mod in out:
+        close(out[mod]['mu'].detach().cpu(), g['mu_' + mod], VAL_RTOL, 'mu_' + mod)
+        close(out[mod]['sigma'].detach().cpu(), g['sigma_' + mod], VAL_RTOL, 'sigma_' + mod)
+        lp = losses.get_normal_log_prob(out[mod]['mu'].unsqueeze(1), out[mod]['sigma'].unsqueeze(1),
+                                        dense(data[mod]), dense(masks[mod]))
+        assert lp.shape == (lat.shape[0],)
+        close(lp.detach().cpu(), g['lp_' + mod], VAL_RTOL, 'lp_' + mod)
+
+    def word_fn(latents, word_weights, sent_embeddings, mask):          # reference simplesif.py:527-537
+        return losses.get_word_log_prob_angular2(latents, t['We'], word_weights, sent_embeddings, mask, 1e-3)
+    total = losses.get_log_prob_matrix(dict(cfg['args']), lat, out, data, masks, word_fn)
+    close(total.detach().cpu(), g['total'], VAL_RTOL, 'total')
+    loss = (-total).mean()
+    loss.backward()
+    close(loss.detach().cpu(), g['loss'], VAL_RTOL, 'loss')
+    close(lat.grad.cpu(), g['grad_latents'], GRAD_RTOL, 'grad_latents')
+    for mod in out:
+        for nm in ('mu', 'log_sigma'):
+            layer = model.embed2out[mod][nm]
+            gW = layer.weight.grad.cpu().numpy()
+            want = g['gW_%s_%s' % (nm, mod)]
+            close(gW[:want.shape[0]], want, GRAD_RTOL, 'gW_%s_%s' % (nm, mod))
+            chk, wchk = cases.checksum(gW), g['gWsum_%s_%s' % (nm, mod)]
+            np.testing.assert_allclose(chk[:2], wchk[:2], rtol=2e-3, atol=2e-3 * abs(wchk[1]))
+            close(layer.bias.grad.cpu(), g['gb_%s_%s' % (nm, mod)], GRAD_RTOL, 'gb_%s_%s' % (nm, mod))
+    if model.norm is not None:
+        close(model.norm.weight.grad.cpu(), g['g_norm_w'], GRAD_RTOL, 'g_norm_w')
+        close(model.norm.bias.grad.cpu(), g['g_norm_b'], GRAD_RTOL, 'g_norm_b')
+
+
+@pytest.mark.parametrize('tag', list(cases.MMB_CASES))
+def test_word_term_value_and_grad(mods, golden_dir, tag):
+    torch, losses, models = mods
+    g = np.load(os.path.join(golden_dir, 'mmb_%s.npz' % tag))
+    cfg, c, t, model, data, masks = build(torch, models, losses, tag, True)
+    lat = t['latents'].clone().requires_grad_(True)
+    lp = losses.get_word_log_prob_angular2(lat, t['We'], t['text_w'], t['text'], t['text_m'], 1e-3)
+    close(lp.detach().cpu(), g['word_lp'], VAL_RTOL, 'word_lp')
+    lp.sum().backward()
+    close(lat.grad.cpu(), g['word_grad'], GRAD_RTOL, 'word_grad')
+    # the float64 oracle agrees with both
+    want = mo.get_word_log_prob_angular2(c['latents'], c['We'], c['text_w'], c['text'], c['text_m'], 1e-3)
+    close(lp.detach().cpu(), want, VAL_RTOL, 'word_lp vs oracle')
+    # 2-D mask (B, L) is accepted as well (only mask[:, :, 0] is used by the reference)
+    lp2 = losses.get_word_log_prob_angular2(t['latents'], t['We'], t['text_w'], t['text'],
+                                            t['text_m'][:, :, 0].contiguous(), 1e-3)
+    assert torch.allclose(lp2, lp.detach())
+
+
+def test_frozen_heads_and_latent_only_grads(mods):
+    """optimize_latents(train=False) / freeze_weights: only the latents receive gradients."""
+    torch, losses, models = mods
+    cfg, c, t, model, data, masks = build(torch, models, losses, 'mmb1_small', True)
+    model.freeze_weights()
+    lat = t['latents'].clone().requires_grad_(True)
+    out = model(lat)
+    total = losses.get_log_prob_matrix({}, lat, out, data, masks,
+                                       lambda l, w, s, m: losses.get_word_log_prob_angular2(l, t['We'], w, s, m, 1e-3))
+    (-total).mean().backward()
+    assert lat.grad is not None and torch.isfinite(lat.grad).all()
+    assert all(p.grad is None for p in model.embed2out.parameters())
+
+
+def test_nonfinite_log_prob_exits(mods):
+    """reference losses.py:258-264: an infinite log-probability prints and sys.exit()s."""
+    torch, losses, models = mods
+    cfg, c, t, model, data, masks = build(torch, models, losses, 'mmb1_small', True)
+    out = model(t['latents'])
+    out['audio']['sigma'] = torch.zeros_like(out['audio']['sigma'])      # sigma = 0 -> -inf / nan
+    with pytest.raises(SystemExit):
+        losses.get_log_prob_matrix({}, t['latents'], out, data, masks,
+                                   lambda l, w, s, m: losses.get_word_log_prob_angular2(l, t['We'], w, s, m, 1e-3))
+
+
+def test_mosi_batch_shapes_130(mods):
+    """Batches beyond one 64-row tile (valid/test use 512, reference simplesif.py:458-459)."""
+    torch, losses, models = mods
+    cfg = dict(cases.MMB_CASES['mmb2_mosi'], B=130, V=300)
+    c = cases.mmb_inputs(**cfg)
+    dev = torch.device('cuda')
+    model = models.AudioVisualGeneratorMultimodal(c['d'], c['A'], c['Vd'], norm='layer_norm',
+                                                  frozen_weights=False).to(dev)
+    cases.load_heads(model, c['heads'], c.get('norm_params'))
+    lat = torch.tensor(c['latents'], device=dev)
+    out = model(lat)
+    want = mo.heads_forward(c['latents'], c['heads'], 'layer_norm', c['norm_params'])
+    for mod in out:
+        close(out[mod]['mu'].detach().cpu(), want[mod]['mu'], VAL_RTOL, mod)
+        close(out[mod]['sigma'].detach().cpu(), want[mod]['sigma'], VAL_RTOL, mod)
+    args = [torch.tensor(c[k], device=dev) for k in ('We', 'text_w', 'text', 'text_m')]
+    wl = losses.get_word_log_prob_angular2(lat, *args, 1e-3)
+    close(wl.cpu(), mo.get_word_log_prob_angular2(c['latents'], c['We'], c['text_w'], c['text'], c['text_m'], 1e-3),
+          VAL_RTOL, 'word 130')
+    wg = mo.word_log_prob_grad(c['latents'], c['We'], c['text_w'], c['text'], c['text_m'], 1e-3)
+    lat2 = lat.clone().requires_grad_(True)
+    losses.get_word_log_prob_angular2(lat2, *args, 1e-3).sum().backward()
+    close(lat2.grad.cpu(), wg, GRAD_RTOL, 'word grad 130')
