@@ -1,0 +1,357 @@
+"""Drop-in for the hot-path part of the reference's ``simplesif.py``.
+
+Kept with the reference's names and signatures: ``update_masks``, ``update_masks_vect``,
+``optimize_latents`` (reference simplesif.py:36-162), ``read_config`` / ``parse_arguments``
+(177-238) and ``main`` (240-916).  The SIF initialisation goes through ``sif.py`` and the
+latent-optimisation loop through ``models.py`` / ``losses.py``, i.e. through libmmb_b200.so.
+
+What changes inside the loop (results do not):
+  * the four ``torch.cat`` of data and four of masks per step (reference 94-113) are
+    ``losses.CatSegments`` -- the fused Gaussian kernel reads the base tensors directly;
+  * the per-modality ``sigma.min()`` / ``lp.min()`` device syncs (reference 82-84 and
+    losses.py:258-264, ~14 per MMB2 step) collapse into one status word per step.
+The reference imports ``analyze_embeddings.get_closest_words``, a module that is not in its
+tree; it is optional here.
+"""
+import argparse
+import json
+import os
+import pprint
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.optim as optim
+from torch.utils.data import DataLoader
+
+from losses import CatSegments, get_log_prob_matrix, get_word_log_prob_angular, get_word_log_prob_dot_prod  # noqa: F401
+from losses import get_word_log_prob_angular2
+from models import AudioVisualGeneratorConcat, AudioVisualGenerator, AudioVisualGeneratorMultimodal  # noqa: F401
+from sentiment_model import SentimentData, SentimentModel, train_sentiment_for_latents
+from sif import load_weights, get_sentence_embeddings
+from utils import load_data, normalize_data, MMData, MMDataExtra, add_positional_embeddings
+
+try:  # not part of the reference tree either
+    from analyze_embeddings import get_closest_words
+except ImportError:  # pragma: no cover
+    get_closest_words = None
+
+
+def update_masks(mask_dict, data, embedding_dim):
+    """reference simplesif.py:36-40 -- text mask = (ids != 0) broadcast to (N, L, embedding_dim)."""
+    tmp = (data != 0).astype(int)
+    mask_dict['text'] = np.broadcast_to(np.expand_dims(tmp, -1), tmp.shape + (embedding_dim,))
+    print(np.all(mask_dict['text'][:, :, 1] == mask_dict['text'][:, :, 0]))
+
+
+def update_masks_vect(mask_dict, data, key='text'):
+    """reference simplesif.py:42-47 -- a time step is valid iff no feature of it is exactly 0."""
+    tmp2 = np.all(data != 0, axis=-1).astype(int)
+    print(tmp2.shape)
+    mask_dict[key] = np.broadcast_to(np.expand_dims(tmp2, -1), data.shape)
+
+
+def _batch_dicts(args, x):
+    """The per-step ``batch_data`` / ``batch_masks`` of reference simplesif.py:72-124, with the
+    concatenated modalities expressed as CatSegments instead of materialised torch.cat."""
+    if args['dataset'] == 'mosi':
+        j, text, aud, vis, text_m, aud_m, vis_m, text_w = x
+        text_gauss, text_gauss_m = text, text_m
+    else:
+        j, text, aud, vis, text_m, aud_m, vis_m, text_w, text_gauss, text_gauss_m = x
+    batch_data = {'text': text, 'audio': aud, 'visual': vis, 'text_weights': text_w}
+    batch_masks = {'text': text_m, 'audio': aud_m, 'visual': vis_m}
+    if not args['unimodal']:
+        batch_data.update({
+            'audiovisual': CatSegments([aud, vis]),
+            'textaudio': CatSegments([text_gauss, aud]),
+            'textvisual': CatSegments([text_gauss, vis]),
+            'textaudiovisual': CatSegments([text_gauss, aud, vis]),
+        })
+        batch_masks.update({
+            'audiovisual': CatSegments([aud_m, vis_m]),
+            'textaudio': CatSegments([text_gauss_m, aud_m]),
+            'textvisual': CatSegments([text_gauss_m, vis_m]),
+            'textaudiovisual': CatSegments([text_gauss_m, aud_m, vis_m]),
+        })
+    return j, batch_data, batch_masks
+
+
+def _make_optimizer(args, params, lr):
+    if args['optimizer'] == 'sgd':
+        return optim.SGD(params, lr=lr)
+    elif args['optimizer'] == 'adam':
+        return optim.Adam(params, lr=lr)
+    raise NotImplementedError(args['optimizer'])
+
+
+def _warn_tiny_sigma(out):
+    """reference simplesif.py:82-84, one device sync for all modalities instead of one each."""
+    smallest = torch.stack([d['sigma'].min() for d in out.values()]).min()
+    if float(smallest.abs()) < 1e-7:
+        print({m: float(d['sigma'].min()) for m, d in out.items()}, "boo!")
+
+
+def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epochs, lr, word_prob_fn,
+                     device, validation_data=None, verbose=True):
+    """reference simplesif.py:49-162.
+
+    Minimises ``mean_b(-log p(text, audio, visual | latent_b))`` over the latent matrix (and
+    the generator heads when ``train`` and not ``args['freeze_weights']``) with SGD/Adam.
+    Returns ``(embeddings (N, d) float32 on device, (losses, all_valid_losses))``.
+    """
+    embeddings = torch.tensor(np.array(embed_arr, copy=True), device=device, dtype=torch.float32)
+    embeddings.requires_grad = True
+
+    grad_params = [embeddings]
+    if train and not args['freeze_weights']:
+        grad_params.extend(gen_model.parameters())
+    optimizer = _make_optimizer(args, grad_params, lr)
+
+    valid_niter = 10
+    start_time = time.time()
+    losses = []
+    all_valid_losses = []
+    for i in range(n_epochs):
+        epoch_loss = torch.zeros((), device=device)
+        iters = 0
+        for x in dataloader:
+            j, batch_data, batch_masks = _batch_dicts(args, x)
+            iters += 1
+            optimizer.zero_grad()
+            out = gen_model(embeddings[j])
+            if verbose and i % valid_niter == 0 and iters == 1:
+                _warn_tiny_sigma(out)
+            log_prob = -get_log_prob_matrix(args, embeddings[j], out, batch_data, batch_masks, word_prob_fn,
+                                            device=device, verbose=False)
+            avg_log_prob = log_prob.mean()
+            avg_log_prob.backward()
+            optimizer.step()
+            epoch_loss += avg_log_prob.detach()
+        losses.append(float(epoch_loss))
+        if i % valid_niter == 0:
+            if verbose:
+                print("epoch {}: {} ({}s)".format(i, losses[-1] / max(iters, 1), time.time() - start_time))
+            if validation_data is not None and i % (valid_niter * 8) == 0:
+                valid_embedding, valid_dataloader = validation_data
+                _, valid_losses = optimize_latents(args, False, gen_model, valid_embedding, valid_dataloader,
+                                                   n_epochs, lr, word_prob_fn, device, verbose=False)
+                print("Validation loss:", valid_losses[0][-1])
+                all_valid_losses.append(valid_losses[0][-1])
+
+    if validation_data is not None:  # final validation
+        valid_embedding, valid_dataloader = validation_data
+        _, valid_losses = optimize_latents(args, False, gen_model, valid_embedding, valid_dataloader,
+                                           n_epochs, lr, word_prob_fn, device, verbose=False)
+        print("(Final) Validation loss:", valid_losses[0][-1])
+        all_valid_losses.append(valid_losses[0][-1])
+
+    embeddings.requires_grad = False
+    return embeddings, (losses, all_valid_losses)
+
+
+def make_word_log_prob_fn(args, weights, word_embeddings, a=1e-3):
+    """The ``get_word_log_prob2`` closure of reference simplesif.py:505-537."""
+    if args['word_sim_metric'] == 'angular':
+        word_log_prob_fn = get_word_log_prob_angular2
+    elif args['word_sim_metric'] == 'dot_prod':
+        word_log_prob_fn = get_word_log_prob_dot_prod
+    else:
+        raise NotImplementedError
+
+    def get_word_log_prob2(latents, word_weights, sent_embeddings, mask):
+        # the inf check of reference 529-535 is the kernel's status word (losses.py)
+        return word_log_prob_fn(latents, word_embeddings, word_weights, sent_embeddings, mask, a)
+    return get_word_log_prob2
+
+
+def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, senti_train_data, senti_mask,
+                     word_prob_fn, device, n_epochs=None, verbose=True):
+    """The e2e loop of reference simplesif.py:694-790: latents, generator heads and the
+    sentiment regressor are optimised jointly on
+    ``likelihood_weight * (-log p) + (1 - likelihood_weight) * L1(sentiment) * senti_mask``."""
+    train_embed = torch.tensor(np.array(train_embedding, copy=True), device=device, dtype=torch.float32)
+    train_embed.requires_grad = True
+    grad_params = [train_embed] + list(gen_model.parameters()) + list(senti_model.parameters())
+    optimizer = _make_optimizer(args, grad_params, args['lr'])
+    loss_function = nn.L1Loss(reduction='none')
+    like_w = args['likelihood_weight']
+    train_losses = []
+    start_time = time.time()
+    for i in range(n_epochs if n_epochs is not None else args['n_epochs']):
+        epoch_loss = torch.zeros((), device=device)
+        iters = 0
+        for x in dataloader:
+            j, batch_data, batch_masks = _batch_dicts(args, x)
+            _, s_data = senti_train_data[j]
+            iters += 1
+            optimizer.zero_grad()
+            out = gen_model(train_embed[j])
+            log_prob = -get_log_prob_matrix(args, train_embed[j], out, batch_data, batch_masks, word_prob_fn,
+                                            device=device, verbose=False)
+            senti_loss = loss_function(senti_model(train_embed[j]), s_data)
+            if senti_loss.dim() > 1:
+                senti_loss = senti_loss.mean(-1)
+            senti_loss = senti_loss * senti_mask[j].reshape(senti_loss.shape)
+            loss = (like_w * log_prob + (1. - like_w) * senti_loss).mean()
+            loss.backward()
+            optimizer.step()
+            epoch_loss += loss.detach()
+        train_losses.append(float(epoch_loss))
+        if verbose and i % 10 == 0:
+            print("epoch {}: {} ({}s)".format(i, train_losses[-1] / max(iters, 1), time.time() - start_time))
+    train_embed.requires_grad = False
+    return train_embed, train_losses
+
+
+def read_config(config_file):
+    """reference simplesif.py:177-184."""
+    config = json.load(open(config_file, 'r'))
+    pprint.PrettyPrinter(indent=2).pprint(config)
+    return config
+
+
+def parse_arguments(argv=None):
+    """reference simplesif.py:186-238 -- same flags; the JSON config is merged over them and
+    ``--pos_embed_dim`` / ``--e2e`` / ``--sentiment_epochs`` override it."""
+    parser = argparse.ArgumentParser()
+    parser.add_argument('config_file', help='JSON file containing hyperparameters for model')
+    parser.add_argument('dataset', choices=['mosi', 'pom', 'iemocap'])
+    parser.add_argument('--unimodal', action='store_true', help='run mmb1 (unimodal factorization)')
+    parser.add_argument('--pos_embed_dim', type=int)
+    parser.add_argument('--batch_size', type=int, default=64)
+    parser.add_argument('--n_runs', type=int, default=1)
+    parser.add_argument('--semi_sup_idxes', choices=['{:.1f}'.format(x) for x in np.arange(0.1, 1, 0.1)])
+    parser.add_argument('--config_name', help='override config name in config file')
+    parser.add_argument('--lr_decay', type=float, default=0.5)
+    parser.add_argument('--early_stopping', action='store_true',
+                        help='early stopping when training sentiment model')
+    parser.add_argument('--sentiment_epochs', type=int)
+    parser.add_argument('--emotion', choices=['happy', 'angry', 'neutral', 'sad'], help='iemocap emotion')
+    parser.add_argument('--optimizer', choices=['sgd', 'adam'], default='sgd')
+    parser.add_argument('--norm', choices=['layer_norm', 'batch_norm'])
+    parser.add_argument('--likelihood_weight', type=float)
+    parser.add_argument('--e2e', choices=['y', 'n'], help='end-to-end training of latent variables')
+    parser.add_argument('--time_test', action='store_true', help='Run inference timing')
+    parser.add_argument('--cuda_device', type=int, choices=list(range(8)), help='set CUDA device number')
+    parser.add_argument('--cuda', action='store_true')
+    args = vars(parser.parse_args(argv))
+
+    override_dict = {}
+    if args['pos_embed_dim'] is not None:
+        override_dict['pos_embed_dim'] = args['pos_embed_dim']
+    if args['e2e'] is not None:
+        override_dict['e2e'] = args['e2e']
+    config = read_config(args['config_file'])
+    print('######################################')
+    print("Config: {}".format(config['config_num']))
+    args.update(config)
+    args.update(override_dict)
+    if args['e2e'] == 'y':
+        args['e2e'] = True
+    elif args['e2e'] == 'n':
+        args['e2e'] = False
+    if args['sentiment_epochs']:
+        args['n_sentiment_epochs'] = args['sentiment_epochs']
+    return args
+
+
+def prepare_splits(args, word_embeddings, weights, splits, masks, device):
+    """reference simplesif.py:296-399: SIF initialisation per split (PC removed per split),
+    id -> vector expansion, positional features on audio / visual."""
+    id_key = 'text' if args['dataset'] == 'mosi' else 'text_id'
+    embeddings = [get_sentence_embeddings(word_embeddings, weights, s[id_key]) for s in splits]
+    w_t = torch.tensor(weights, device=device, dtype=torch.float32)
+    we_t = torch.tensor(word_embeddings, device=device, dtype=torch.float32)
+    for s, m in zip(splits, masks):
+        ids = torch.as_tensor(s[id_key], device=device)
+        if args['dataset'] == 'mosi':
+            s['text_id'] = s['text']
+        else:
+            s['text_align'] = s['text']
+            update_masks_vect(m, s['text_align'], 'text_align')
+        s['text'] = we_t[ids]
+        s['text_weights'] = w_t[ids]
+        if args.get('pos_embed_dim', 0) and args['pos_embed_dim'] > 0:
+            n_points, seq_len = m['covarep'].shape[:2]
+            ext = np.ones((n_points, seq_len, args['pos_embed_dim']), dtype=np.int64)
+            for k in ('covarep', 'facet'):
+                s[k] = add_positional_embeddings(args, s[k])
+                m[k] = np.concatenate([m[k], ext], axis=-1)
+    return embeddings, w_t, we_t
+
+
+def main(argv=None):
+    """reference simplesif.py:240-916, for the datasets the reference's loaders can open."""
+    args = parse_arguments(argv)
+    if args['cuda_device'] is not None:
+        os.environ['CUDA_VISIBLE_DEVICES'] = str(args['cuda_device'])
+    if not torch.cuda.is_available():
+        raise RuntimeError('this implementation runs on a CUDA device (sm_100a) only')
+    device = torch.device('cuda')
+
+    word2ix, word_embeddings, data = load_data(args)
+    splits = list(data)
+    masks = []
+    for k in range(3):
+        splits[k], m = normalize_data(splits[k])
+        update_masks(m, splits[k]['text' if args['dataset'] == 'mosi' else 'text_id'], word_embeddings.shape[-1])
+        masks.append(m)
+    weights = load_weights(args)
+    if args['word_sim_metric'] == 'dot_prod':
+        word_embeddings = word_embeddings / np.linalg.norm(word_embeddings, axis=-1, keepdims=True)
+    embeddings, w_t, we_t = prepare_splits(args, word_embeddings, weights, splits, masks, device)
+    train, valid, test = splits
+
+    def dataset(s, m):
+        if args['dataset'] == 'mosi':
+            return MMData(s['text'], s['covarep'], s['facet'], m, s['text_weights'], device)
+        return MMDataExtra(s['text'], s['covarep'], s['facet'], m, s['text_weights'], s['text_align'], device)
+    bs = args['batch_size']
+    loaders = [DataLoader(dataset(train, masks[0]), batch_size=bs, shuffle=True),
+               DataLoader(dataset(valid, masks[1]), batch_size=bs * 8),
+               DataLoader(dataset(test, masks[2]), batch_size=bs * 8)]
+    word_fn = make_word_log_prob_fn(args, w_t, we_t)
+    d, A, Vd = train['text'].shape[-1], train['covarep'].shape[-1], train['facet'].shape[-1]
+    sentiment_data = (train['label'], valid['label'], test['label'])
+
+    for r in range(args['n_runs']):
+        config_name = args['config_name'] or os.path.split(os.path.split(args['config_file'])[0])[1]
+        folder = 'model_saves/{}/config_{}_run_{}'.format(config_name, args['config_num'], r)
+        for sub in ('pre', 'post'):
+            os.makedirs(os.path.join(folder, sub), exist_ok=True)
+        json.dump(args, open(os.path.join(folder, 'config.json'), 'w'), indent=2)
+        torch.save(torch.tensor(np.concatenate(embeddings, axis=0), device=device, dtype=torch.float32),
+                   os.path.join(folder, 'pre', 'embed.bin'))
+        gen_model = AudioVisualGeneratorMultimodal(d, A, Vd, norm=args['norm'], frozen_weights=args['freeze_weights'],
+                                                   unimodal=args['unimodal']).to(device)
+        n_epochs, lr = args['n_epochs'], args['lr']
+        if args['e2e']:
+            n_out = 1 if train['label'].ndim == 1 else train['label'].shape[-1]
+            senti_model = SentimentModel(d, args['sentiment_hidden_size'], n_out).to(device)
+            senti_mask = torch.ones(len(train['label']), device=device)
+            train_embed, train_losses = train_end_to_end(args, gen_model, senti_model, embeddings[0], loaders[0],
+                                                         SentimentData(train['label'], device), senti_mask,
+                                                         word_fn, device)
+            valid_losses = []
+        else:
+            train_embed, (train_losses, valid_losses) = optimize_latents(
+                args, True, gen_model, embeddings[0], loaders[0], n_epochs, lr, word_fn, device,
+                validation_data=(embeddings[1], loaders[1]))
+        valid_embed, _ = optimize_latents(args, False, gen_model, embeddings[1], loaders[1], n_epochs, lr,
+                                          word_fn, device)
+        test_embed, (test_losses, _) = optimize_latents(args, False, gen_model, embeddings[2], loaders[2], n_epochs,
+                                                        lr, word_fn, device)
+        for name, vals in (('embed_loss.txt', train_losses), ('embed_valid_loss.txt', valid_losses),
+                           ('embed_test_loss.txt', test_losses)):
+            with open(os.path.join(folder, name), 'w') as f:
+                f.writelines('{}\n'.format(v) for v in vals)
+        torch.save(torch.cat([train_embed, valid_embed, test_embed], dim=0), os.path.join(folder, 'post', 'embed.bin'))
+        train_sentiment_for_latents(args, (train_embed, valid_embed, test_embed), sentiment_data, device,
+                                    model_save_path=os.path.join(folder, 'post'))
+
+
+if __name__ == '__main__':
+    main()

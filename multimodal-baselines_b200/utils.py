@@ -1,0 +1,102 @@
+"""Data helpers on either side of the hot path (reference utils.py).
+
+``MMData`` / ``MMDataExtra`` define the batch tuple layout the MMB step consumes (reference
+utils.py:193-251) and are kept as in the reference: device-resident tensors, ``__getitem__``
+returns ``(idx, text, aud, vis, text_m, aud_m, vis_m, text_w[, text_a, text_a_m])``.
+``normalize_data`` and ``add_positional_embeddings`` reproduce the reference's preprocessing
+including its quirks (see the docstrings).  The ``.h5`` loaders need ``h5py`` and the external
+datasets, neither of which ships with the reference; they raise a clear error when missing.
+"""
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+
+def load_data(args):
+    """reference utils.py:10-128 -- reads data/{mosi,pom,iemocap}_data.h5 (external downloads,
+    reference README.md:9) and the GloVe / id files (reference .MISSING_LARGE_BLOBS)."""
+    try:
+        import h5py  # noqa: F401
+    except ImportError as e:
+        raise ImportError("load_data needs h5py and the reference's external data files "
+                          "(data/%s_data.h5); neither is part of this repository" % args.get('dataset')) from e
+    if args['dataset'] not in ('mosi', 'pom', 'iemocap'):
+        raise ValueError('unknown dataset %r' % (args['dataset'],))
+    raise FileNotFoundError("data/%s_data.h5 is an external download of the reference and is not available here"
+                            % args['dataset'])
+
+
+def add_positional_embeddings(args, data):
+    """reference utils.py:130-153.
+
+    Appends ``pos_embed_dim`` position features to ``data`` (n_points, seq_len, F).  Quirk kept
+    (SURVEY.md §8d): the sin/cos transform is applied by indexing the FIRST axis
+    (``idxes[2*i, :]``), i.e. only data points ``0 .. pos_embed_dim-1`` get sinusoidal features;
+    every other data point gets the raw position index ``0 .. seq_len-1`` in every new column.
+    """
+    n_points, seq_len = data.shape[0], data.shape[1]
+    pos_embed_dim = args['pos_embed_dim']
+    idxes = np.tile(np.arange(seq_len, dtype=np.float32), [n_points, pos_embed_dim, 1]).transpose([0, 2, 1])
+    for i in range(pos_embed_dim // 2):
+        scale = 10000 ** (2 * i / pos_embed_dim)
+        idxes[2 * i, :] = np.sin(idxes[2 * i, :] / scale)
+        idxes[2 * i + 1, :] = np.cos(idxes[2 * i + 1, :] / scale)
+    return np.concatenate([data, idxes], axis=-1)
+
+
+def normalize_data(train):
+    """reference utils.py:155-191: drop constant audio features, build masks from exact zeros,
+    scale audio / visual features with the split's own min / max (the reference ADDS the
+    minimum -- ``(x + min) * 2 / (max - min) - 1`` -- kept as is), set padding to -10."""
+    audio_diff = train['covarep'].max((0, 1)) - train['covarep'].min((0, 1))
+    train['covarep'] = train['covarep'][:, :, audio_diff.nonzero()[0]]
+    audio_pad, vis_pad = train['covarep'] == 0, train['facet'] == 0
+    audio_mask, vis_mask = (~audio_pad).astype(int), (~vis_pad).astype(int)
+    audio_min, audio_max = train['covarep'].min((0, 1)), train['covarep'].max((0, 1))
+    vis_min, vis_max = train['facet'].min((0, 1)), train['facet'].max((0, 1))
+    train['covarep'] = (train['covarep'] + audio_min) * 2. / (audio_max - audio_min) - 1.
+    train['facet'] = (train['facet'] + vis_min) * 2. / (vis_max - vis_min) - 1.
+    train['covarep'][audio_pad] = -10.
+    train['facet'][vis_pad] = -10.
+    return train, {'covarep': audio_mask, 'facet': vis_mask}
+
+
+def _as_f32(x, device):
+    return x if torch.is_tensor(x) else torch.tensor(x, device=device, dtype=torch.float32)
+
+
+class MMData(Dataset):
+    """reference utils.py:193-233."""
+
+    def __init__(self, text, audio, visual, masks, text_weights, device):
+        super(Dataset, self).__init__()
+        self.text = _as_f32(text, device)
+        self.text_weights = _as_f32(text_weights, device)
+        self.audio = _as_f32(audio, device)
+        self.visual = _as_f32(visual, device)
+        assert self.text.size()[0] == self.audio.size()[0]
+        assert self.audio.size()[0] == self.visual.size()[0]
+        assert self.text.size()[0] == self.text_weights.size()[0]
+        self.text_mask = _as_f32(masks['text'], device)
+        self.audio_mask = _as_f32(masks['covarep'], device)
+        self.visual_mask = _as_f32(masks['facet'], device)
+        self.len = self.text.size()[0]
+
+    def __len__(self):
+        return self.len
+
+    def __getitem__(self, idx):
+        return (idx, self.text[idx], self.audio[idx], self.visual[idx], self.text_mask[idx],
+                self.audio_mask[idx], self.visual_mask[idx], self.text_weights[idx])
+
+
+class MMDataExtra(MMData):
+    """reference utils.py:235-251 -- adds the aligned text vectors + mask (POM / IEMOCAP)."""
+
+    def __init__(self, text, audio, visual, masks, text_weights, text_aligned, device):
+        super(MMDataExtra, self).__init__(text, audio, visual, masks, text_weights, device)
+        self.text_aligned = _as_f32(text_aligned, device)
+        self.text_aligned_mask = _as_f32(masks['text_align'], device)
+
+    def __getitem__(self, idx):
+        return MMData.__getitem__(self, idx) + (self.text_aligned[idx], self.text_aligned_mask[idx])

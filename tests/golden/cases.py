@@ -147,3 +147,30 @@ def load_heads(model, heads, norm_params=None):
         if norm_params is not None and model.norm is not None:
             model.norm.weight.copy_(torch.tensor(norm_params[0]))
             model.norm.bias.copy_(torch.tensor(norm_params[1]))
+
+
+# optimize_latents (reference simplesif.py:49-162) end-to-end cases: fixed batch order.
+OPT_CASES = {
+    'sgd_train': dict(inputs=dict(B=12, T=5, d=24, A=6, Vd=5, V=40, seed=41, norm='layer_norm', unimodal=False,
+                                  args={}),
+                      args={'dataset': 'mosi', 'unimodal': False, 'freeze_weights': False, 'optimizer': 'sgd',
+                            'word_loss_weight': 0.2},
+                      train=True, batch=4, epochs=4, lr=0.01),
+    'adam_infer': dict(inputs=dict(B=10, T=4, d=24, A=5, Vd=4, V=30, seed=42, norm=None, unimodal=True, args={}),
+                       args={'dataset': 'mosi', 'unimodal': True, 'freeze_weights': True, 'optimizer': 'adam'},
+                       train=False, batch=5, epochs=3, lr=0.01),
+}
+
+
+def raw_split(n=7, T=6, A=9, Vd=5, seed=51):
+    """A raw (un-normalised) split like the reference's h5 arrays: exact zeros mark padding,
+    audio feature 3 is constant (normalize_data drops it)."""
+    rng = np.random.default_rng(seed)
+    cov = rng.normal(size=(n, T, A)) * 3 + 1
+    fac = rng.normal(size=(n, T, Vd)) * 2 - 1
+    lens = rng.integers(2, T + 1, size=n)
+    pad = np.arange(T)[None, :, None] >= lens[:, None, None]
+    cov[:, :, 3] = 0.0
+    cov[np.broadcast_to(pad, cov.shape)] = 0.0
+    fac[np.broadcast_to(pad, fac.shape)] = 0.0
+    return {'covarep': cov, 'facet': fac}

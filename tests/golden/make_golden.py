@@ -144,5 +144,55 @@ def main():
         save('mmb_%s.npz' % tag, **res)
 
 
+def golden_optimize_latents():
+    """Run the reference's own optimize_latents (simplesif.py:49-162, executed from the source
+    file -- the module itself cannot be imported) on a small MOSI-shaped
+    problem with a fixed batch order, for train=True (SGD on latents + heads) and train=False."""
+    import time
+    import torch.optim as optim
+    from torch.utils.data import DataLoader
+    import utils_stub
+    src = open(os.path.join(REF, 'simplesif.py')).read().split('\n')
+    code = '\n'.join(src[48:162])
+    ns = {'torch': torch, 'optim': optim, 'time': time, 'np': np,
+          'get_log_prob_matrix': ref_losses.get_log_prob_matrix}
+    exec(compile(code, 'reference simplesif.py:49-162', 'exec'), ns)
+    ref_optimize_latents = ns['optimize_latents']
+    out = {}
+    for tag, cfg in cases.OPT_CASES.items():
+        c = cases.mmb_inputs(**cfg['inputs'])
+        torch.manual_seed(0)
+        model = ref_models.AudioVisualGeneratorMultimodal(c['d'], c['A'], c['Vd'], norm=cfg['inputs']['norm'],
+                                                          frozen_weights=False, unimodal=cfg['inputs']['unimodal'])
+        cases.load_heads(model, c['heads'], c.get('norm_params'))
+        ds = utils_stub.MMData(c['text'], c['aud'], c['vis'], {'text': c['text_m'], 'covarep': c['aud_m'],
+                                                                'facet': c['vis_m']}, c['text_w'], torch.device('cpu'))
+        loader = DataLoader(ds, batch_size=cfg['batch'], shuffle=False)
+        We_t = torch.tensor(c['We'])
+
+        def word_fn(latents, word_weights, sent_embeddings, mask):
+            return ref_losses.get_word_log_prob_angular2(latents, We_t, word_weights, sent_embeddings, mask, 1e-3)
+        args = dict(cfg['args'])
+        emb, (losses, _) = ref_optimize_latents(args, cfg['train'], model, c['latents'], loader, cfg['epochs'],
+                                                cfg['lr'], word_fn, torch.device('cpu'), verbose=False)
+        out[tag + '_emb'] = emb.detach().numpy()
+        out[tag + '_losses'] = np.array(losses)
+        out[tag + '_Wmu_audio'] = model.embed2out['audio']['mu'].weight.detach().numpy()
+    save('optimize_latents.npz', **out)
+
+
+def golden_utils():
+    """Reference utils.py preprocessing (normalize_data 155-191, add_positional_embeddings
+    130-153, quirks included) on a small seeded split."""
+    import utils_stub
+    split = cases.raw_split()
+    pos = utils_stub.add_positional_embeddings({'pos_embed_dim': 4}, split['covarep'].copy())
+    norm, masks = utils_stub.normalize_data({k: v.copy() for k, v in split.items()})
+    save('utils.npz', pos=pos, covarep=norm['covarep'], facet=norm['facet'], m_covarep=masks['covarep'],
+         m_facet=masks['facet'])
+
+
 if __name__ == '__main__':
     main()
+    golden_optimize_latents()
+    golden_utils()

@@ -1,0 +1,100 @@
+"""CPU: host-side logic of the drop-in modules that needs no GPU -- data preparation
+(reference utils.py quirks), config parsing, metrics, start block, module surfaces."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+
+def test_utils_match_reference(golden_dir):
+    import utils
+    g = np.load(os.path.join(golden_dir, 'utils.npz'))
+    split = cases.raw_split()
+    pos = utils.add_positional_embeddings({'pos_embed_dim': 4}, split['covarep'].copy())
+    np.testing.assert_array_equal(pos, g['pos'])
+    # the quirk: only the first pos_embed_dim data points get sin/cos, the rest raw positions
+    np.testing.assert_array_equal(pos[5, :, -1], np.arange(pos.shape[1]))
+    norm, masks = utils.normalize_data({k: v.copy() for k, v in split.items()})
+    np.testing.assert_array_equal(norm['covarep'], g['covarep'])
+    np.testing.assert_array_equal(norm['facet'], g['facet'])
+    np.testing.assert_array_equal(masks['covarep'], g['m_covarep'])
+    np.testing.assert_array_equal(masks['facet'], g['m_facet'])
+    assert norm['covarep'].shape[-1] == split['covarep'].shape[-1] - 1       # constant feature dropped
+
+
+def test_start_block_is_sklearns():
+    import sif_functions
+    from oracle import sif_oracle as so
+    np.testing.assert_array_equal(sif_functions.start_block(300, 1), so.start_block(300, 1))
+    assert sif_functions.start_block(40, 3).shape == (40, 13)
+
+
+def test_module_surface_matches_reference_imports():
+    """The names the reference imports from each module exist here."""
+    import sif_functions, sif, losses, models, simplesif, utils, sentiment_model  # noqa: E401
+    for mod, names in (
+        (sif_functions, 'Params seq2weight SIF_embedding get_weighted_average compute_pc remove_pc'),
+        (sif, 'load_weights get_sentence_embeddings get_sentence_word_weights get_word_weights'),
+        (losses, 'get_log_prob_matrix get_word_log_prob_angular get_word_log_prob_dot_prod '
+                 'get_word_log_prob_angular2 get_normal_log_prob full_loss iemocap_loss pom_loss'),
+        (models, 'AudioVisualGeneratorConcat AudioVisualGenerator AudioVisualGeneratorMultimodal'),
+        (simplesif, 'optimize_latents update_masks update_masks_vect read_config parse_arguments main'),
+        (utils, 'load_data normalize_data MMData MMDataExtra add_positional_embeddings'),
+        (sentiment_model, 'SentimentData SentimentModel train_sentiment_for_latents'),
+    ):
+        for n in names.split():
+            assert hasattr(mod, n), (mod.__name__, n)
+
+
+def test_generator_module_layout():
+    import models
+    m = models.AudioVisualGeneratorMultimodal(300, 76, 49, norm='layer_norm', frozen_weights=False)
+    assert list(m.embed2out.keys()) == ['audio', 'visual', 'audiovisual', 'textaudio', 'textvisual',
+                                        'textaudiovisual']
+    assert m.embed2out['textaudiovisual']['mu'].weight.shape == (425, 300)
+    assert sum(p.numel() for p in m.parameters()) == 843400
+    m1 = models.AudioVisualGeneratorMultimodal(300, 76, 49, unimodal=True)
+    assert sum(p.numel() for p in m1.parameters()) == 75250
+    assert not any(p.requires_grad for p in m1.embed2out.parameters())   # frozen by default
+    with pytest.raises(NotImplementedError):
+        models.AudioVisualGeneratorMultimodal(8, 2, 2, norm='group_norm')
+
+
+def test_parse_arguments_merges_config(tmp_path):
+    import simplesif
+    cfg = {'config_num': 3, 'lr': 0.01, 'n_epochs': 100, 'optimizer': 'adam', 'norm': 'layer_norm', 'e2e': True,
+           'pos_embed_dim': 2, 'n_sentiment_epochs': 50}
+    f = tmp_path / 'cfg' / 'config_3.json'
+    f.parent.mkdir()
+    f.write_text(json.dumps(cfg))
+    args = simplesif.parse_arguments([str(f), 'mosi', '--unimodal', '--pos_embed_dim', '4', '--e2e', 'n',
+                                      '--sentiment_epochs', '7'])
+    assert args['dataset'] == 'mosi' and args['unimodal'] is True
+    assert args['optimizer'] == 'adam'            # the JSON wins over the flag default (reference 228-229)
+    assert args['pos_embed_dim'] == 4 and args['e2e'] is False and args['n_sentiment_epochs'] == 7
+
+
+def test_update_masks():
+    import simplesif
+    ids = np.array([[3, 0, 5], [0, 0, 1]])
+    m = {}
+    simplesif.update_masks(m, ids, 4)
+    assert m['text'].shape == (2, 3, 4)
+    np.testing.assert_array_equal(m['text'][:, :, 0], (ids != 0).astype(int))
+    x = np.ones((2, 3, 2))
+    x[0, 1, 1] = 0
+    simplesif.update_masks_vect(m, x, 'text_align')
+    np.testing.assert_array_equal(m['text_align'][:, :, 0], [[1, 0, 1], [1, 1, 1]])
+
+
+def test_metrics_keys():
+    import losses
+    rng = np.random.default_rng(0)
+    y = rng.uniform(-3, 3, 50)
+    r = losses.full_loss(y + 0.1 * rng.standard_normal(50), y)
+    assert set(r) == {'mae', 'accuracy', 'corr', 'mult_acc', 'f_score', 'confusion_matrix', 'class_report'}
+    r = losses.pom_loss(rng.uniform(1, 7, (20, 3)), rng.uniform(1, 7, (20, 3)))
+    assert set(r) == {'mae', 'corr', 'mult_acc', 'f_score'} and len(r['mae']) == 3

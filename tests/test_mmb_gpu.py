@@ -160,3 +160,31 @@ def test_mosi_batch_shapes_130(mods):
     lat2 = lat.clone().requires_grad_(True)
     losses.get_word_log_prob_angular2(lat2, *args, 1e-3).sum().backward()
     close(lat2.grad.cpu(), wg, GRAD_RTOL, 'word grad 130')
+
+
+@pytest.mark.parametrize('tag', list(cases.OPT_CASES))
+def test_optimize_latents_matches_reference_loop(mods, golden_dir, tag):
+    """simplesif.optimize_latents vs the reference's own loop (simplesif.py:49-162 executed
+    from source when the fixture was generated): same batch order, SGD / Adam, train / infer."""
+    torch, losses, models = mods
+    import simplesif
+    import utils
+    from torch.utils.data import DataLoader
+    g = np.load(os.path.join(golden_dir, 'optimize_latents.npz'))
+    cfg = cases.OPT_CASES[tag]
+    c = cases.mmb_inputs(**cfg['inputs'])
+    dev = torch.device('cuda')
+    model = models.AudioVisualGeneratorMultimodal(c['d'], c['A'], c['Vd'], norm=cfg['inputs']['norm'],
+                                                  frozen_weights=False, unimodal=cfg['inputs']['unimodal']).to(dev)
+    cases.load_heads(model, c['heads'], c.get('norm_params'))
+    ds = utils.MMData(c['text'], c['aud'], c['vis'], {'text': c['text_m'], 'covarep': c['aud_m'],
+                                                       'facet': c['vis_m']}, c['text_w'], dev)
+    loader = DataLoader(ds, batch_size=cfg['batch'], shuffle=False)
+    We_t = torch.tensor(c['We'], device=dev)
+    word_fn = simplesif.make_word_log_prob_fn({'word_sim_metric': 'angular'}, None, We_t)
+    emb, (losses_, _) = simplesif.optimize_latents(dict(cfg['args']), cfg['train'], model, c['latents'], loader,
+                                                   cfg['epochs'], cfg['lr'], word_fn, dev, verbose=False)
+    assert emb.shape == c['latents'].shape and not emb.requires_grad
+    close(np.array(losses_), g[tag + '_losses'], 2e-4, 'losses')
+    close(emb.cpu(), g[tag + '_emb'], 1e-3, 'latents')
+    close(model.embed2out['audio']['mu'].weight.detach().cpu(), g[tag + '_Wmu_audio'], 1e-3, 'W')

@@ -1,0 +1,50 @@
+"""torchrun --nproc-per-node R tools/dist_check.py : the utterance-sharded SIF path over NCCL
+must reproduce the single-GPU result (same PC up to FP32 reduction order, same embeddings)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'multimodal-baselines_b200'))
+import numpy as np
+import torch
+import torch.distributed as dist
+import sif_dist
+import sif_functions as sf
+
+
+def main():
+    rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', rank)))
+    dev = torch.device('cuda')
+    dist.init_process_group('nccl', device_id=dev)
+    ok = True
+    for n_global, L, V in ((100_003, 64, 50_000), (157, 20, 3016)):      # N >= d and N < d (transposed) cases
+        g = torch.Generator(device=dev)
+        g.manual_seed(5)                                                 # same data on every rank
+        table = 0.4 * torch.randn((V, 300), device=dev, generator=g) + 0.3 * torch.randn((1, 300), device=dev, generator=g)
+        table[0] = 0
+        vw = torch.rand(V, device=dev, generator=g) * 0.9 + 0.1
+        ids = torch.randint(1, V, (n_global, L), device=dev, generator=g)
+        lens = torch.randint(1, L + 1, (n_global, 1), device=dev, generator=g)
+        ids[torch.arange(L, device=dev)[None, :] >= lens] = 0
+        lo, hi = sif_dist.shard_bounds(n_global, world, rank)
+        emb_l, pc_l, st = sif_dist.sharded_sif_embedding(table, vw, ids[lo:hi].contiguous(), n_global, lo, npc=1)
+        emb_1, pc_1 = sf.sif_embedding_device(table, vw, ids, npc=1, return_pc=True)
+        cos = float((pc_l[0].double() @ pc_1[0].double()))
+        err = float((emb_l - emb_1[lo:hi]).abs().max() / emb_1.abs().max())
+        pcs = [torch.empty_like(pc_l) for _ in range(world)]
+        dist.all_gather(pcs, pc_l)
+        same = all(torch.equal(pcs[0], p) for p in pcs)                  # replicated solve: identical bits
+        good = cos > 0.99999 and err < 2e-5 and same
+        ok = ok and good
+        print('rank %d N=%d: pc cos %.8f, emb err %.2e, replicas identical %s -> %s'
+              % (rank, n_global, cos, err, same, 'ok' if good else 'FAIL'), flush=True)
+    flag = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    sys.exit(int(flag.item() != 0))
+
+
+if __name__ == '__main__':
+    main()
