@@ -15,8 +15,9 @@ import sif_functions as sf
 
 def main():
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
-    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', rank)))
-    dev = torch.device('cuda')
+    local = int(os.environ.get('LOCAL_RANK', rank))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
     dist.init_process_group('nccl', device_id=dev)
     ok = True
     for n_global, L, V in ((100_003, 64, 50_000), (157, 20, 3016)):      # N >= d and N < d (transposed) cases
