@@ -23,8 +23,9 @@
 //   flush    : the tensor core adds each MMA into the FP32 accumulator with truncation, a bias
 //              of ~1e-7 per MMA that grows linearly with the K chain (measured 1e-4 relative
 //              over 6.7 k rows); every `seg` stages (default 64 = 1024 rows) the workers drain
-//              TMEM (tcgen05.ld) into the CTA's FP32 partial tile in global memory with
-//              round-to-nearest adds, which bounds the bias at ~2e-5 relative.
+//              TMEM (tcgen05.ld) into the CTA's FP32 partial tile in global memory (L2-resident,
+//              column-major so that lane = row gives coalesced lines) with round-to-nearest
+//              adds, which bounds the bias at ~2e-5 relative.
 //   reduce   : a second kernel sums the per-CTA partials in CTA order (deterministic) and
 //              mirrors the upper triangle.
 #include <cuda.h>
@@ -48,34 +49,11 @@ constexpr int kThreads = 192;                   // warp0 TMA, warp1 MMA, warps 2
 constexpr int kColsAB = 480, kColsC = 48;
 constexpr int kPartialStride = 128 * kColsAB + kColsC * kColsC;   // floats per CTA: tiles A|B, then block C
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -250,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int q = warp & 3;          // TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;
     float* part = prm.partial + (size_t)blockIdx.x * kPartialStride;
-    float* out = part + (size_t)row * kColsAB;
+    float* outT = part + row;   // column-major tiles A|B: element (row, c) at part[c * 128 + row]
     // block C: 11 x 11 grid of 4x4 blocks over cols 256..299, upper triangle (66 pairs),
     // dealt round-robin to the four warps.
     const int pidx = lane * 4 + (warp - 2);
@@ -313,23 +291,24 @@ __global__ void __launch_bounds__(kThreads, 1)
       // flush this segment's TMEM accumulators into the FP32 partial (round-to-nearest adds)
       mbar_wait(bar_done, (uint32_t)(sg & 1));
       tc_fence_after();
+      // The partial is stored column-major (column c of tiles A|B = 128 consecutive floats), so
+      // with lane = TMEM lane = tile row every global access of the read-modify-write is one
+      // fully coalesced 128-byte line per warp (a row-major partial costs 32 lines per access).
       for (int c = 0; c < kColsAB; c += 32) {
+        float* o = outT + (size_t)c * 128;
+        float old[32];
+        if (sg > 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) old[j] = o[(size_t)j * 128];
+        }
         uint32_t r[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c, r);
-        float4* o4 = (float4*)(out + c);
         if (sg == 0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          for (int j = 0; j < 32; ++j) o[(size_t)j * 128] = __uint_as_float(r[j]);
         } else {
-          float4 old[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) old[j] = o4[j];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o4[j] = make_float4(old[j].x + __uint_as_float(r[4 * j]), old[j].y + __uint_as_float(r[4 * j + 1]),
-                                old[j].z + __uint_as_float(r[4 * j + 2]), old[j].w + __uint_as_float(r[4 * j + 3]));
+          for (int j = 0; j < 32; ++j) o[(size_t)j * 128] = old[j] + __uint_as_float(r[j]);
         }
       }
       tc_fence_before();
@@ -337,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (lane == 0) mbar_arrive(bar_free);
     }
     if (nseg == 0)
-      for (int c = 0; c < kColsAB; c += 4) *(float4*)(out + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < kColsAB; ++c) outT[(size_t)c * 128] = 0.f;
     if (has_c) {
       float* cpart = part + 128 * kColsAB;   // 48 x 48 block-C region
 #pragma unroll
@@ -357,11 +336,11 @@ __global__ void __launch_bounds__(256)
     gram_tc_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ G) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= kD * kD) return;
-  const int i = idx / kD, j = idx % kD;
+  const int j = idx / kD, i = idx % kD;   // consecutive threads walk a column (coalesced reads)
   if (j < i) return;
   const float* p;
-  if (i < 128) p = partial + (size_t)i * kColsAB + j;
-  else if (i < 256) p = partial + (size_t)(i - 128) * kColsAB + 304 + (j - 128);
+  if (i < 128) p = partial + (size_t)j * 128 + i;
+  else if (i < 256) p = partial + (size_t)(304 + (j - 128)) * 128 + (i - 128);
   else p = partial + 128 * kColsAB + (size_t)(i - 256) * kColsC + (j - 256);
   float s = 0.f;
   for (int c = 0; c < n_cta; ++c) s += p[(size_t)c * kPartialStride];
