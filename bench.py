@@ -47,6 +47,9 @@ ZIPF_S = 1.1
 # algorithmic bytes per utterance of the embed pass at L tokens, d floats:
 # ids L*8 + gathered rows L*d*4 (every token counted, no cache credit) + output d*4.
 EMBED_BYTES_PER_UTT = L_TOK * 8 + L_TOK * DIM * 4 + DIM * 4
+# kernels of libmmb_b200.so per step: embed 1, Gram 2 (tcgen05 + partial reduce), component solve
+# n_iter + 3 = 10 (prep, 8 iterations, final), projection 1
+LAUNCHES_PER_STEP = 14
 WORKLOAD = 'sif_%dM_utt_x%d_tok_v%dk_d%d' % (N_UTT // 1_000_000, L_TOK, VOCAB // 1000, DIM) \
     if N_UTT >= 1_000_000 else 'sif_%d_utt_x%d_tok_v%d_d%d' % (N_UTT, L_TOK, VOCAB, DIM)
 
@@ -375,7 +378,7 @@ def main():
                        'parallelism': 'utterance shards x%d + 1 NCCL all-reduce of the 300x300 Gram' % world,
                        'l2': 'inputs larger than L2 (ids %.1f GB + embeddings %.1f GB per rank, table 0.48 GB)'
                              % (n_local * L_TOK * 8 / 1e9, n_local * DIM * 4 / 1e9)},
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': 5 * args.steps,
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': LAUNCHES_PER_STEP * args.steps,
             'roofline': roofline, 'cpu_baseline': cpu,
         }))
     if world > 1:

@@ -303,6 +303,7 @@ constexpr int kPcmThreads = 320;
 struct PcmSmall {
   double S[kPcMaxK + 1][kPcMaxK + 1];
   double Vv[kPcMaxK][kPcMaxK + 1];
+  double P[kPcMaxK][kPcMaxK + 1];   // scratch of pcm_top1
   double lam[kPcMaxK];
   double rc[kPcMaxK / 2], rs[kPcMaxK / 2];
   double red[8];
@@ -329,39 +330,46 @@ __device__ __forceinline__ double pcm_rcp(double x) {
   return r * fma(-x, r, 2.0);
 }
 
-// Upper Cholesky S = R^T R in place by warp 0, left-looking (lane j >= c forms
-// S[c][j] - sum_{a<c} R[a][c] R[a][j], then scales by 1/R[c][c]).  Columns whose pivot is not
-// positive relative to the largest diagonal entry are dropped (they lie in the span of earlier
-// columns): row c of R becomes 0 and lam[c] = 1/R[c][c] = 0.  Ends with __syncthreads().
-__device__ __forceinline__ void pcm_cholesky(PcmSmall& sm, int k) {
+// Upper Cholesky S = R^T R in place by warp 0, left-looking: for column step c lane j >= c forms
+// v_j = S[c][j] - sum_{a<c} R[a][c] R[a][j] AND the pivot v_c itself (redundantly, so that no
+// value has to cross lanes inside the k-step serial chain), then scales by 1/sqrt(v_c).
+// 1/sqrt comes from the FP32 hardware seed on the pivot scaled into (0, 1] plus `newton`
+// Newton steps in FP64 (1: ~5e-15 relative, enough where only the span of Q matters; 2: full
+// double precision).  Columns whose pivot is not positive relative to the largest diagonal
+// entry are dropped (they lie in the span of earlier columns): row c of R becomes 0 and
+// lam[c] = 1/R[c][c] = 0.  Ends with __syncthreads().
+__device__ __forceinline__ void pcm_cholesky(PcmSmall& sm, int k, int newton) {
   if (threadIdx.x < 32) {
     const int j = threadIdx.x;
-    double dg = (j < k) ? sm.S[j][j] : 0.0;
-    double dmax = dg;
+    double dmax = (j < k) ? sm.S[j][j] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-    const double tiny = 1e-26 * dmax;
+    const bool usable = dmax > 0.0 && dmax < 1e300;
+    const double rs_dmax = usable ? rsqrt(dmax) : 0.0;   // once per factorisation
+    const double inv_dmax = rs_dmax * rs_dmax;
     for (int c = 0; c < k; ++c) {
-      double v0 = 0.0, v1 = 0.0;
+      double vj = 0.0, vc = 0.0;
       if (j >= c && j < k) {
-        v0 = sm.S[c][j];
-        int a = 0;
-        for (; a + 1 < c; a += 2) {
-          v0 = fma(-sm.S[a][c], sm.S[a][j], v0);
-          v1 = fma(-sm.S[a + 1][c], sm.S[a + 1][j], v1);
+        vj = sm.S[c][j];
+        vc = sm.S[c][c];
+        for (int a = 0; a < c; ++a) {
+          const double rac = sm.S[a][c];
+          vj = fma(-rac, sm.S[a][j], vj);
+          vc = fma(-rac, rac, vc);
         }
-        if (a < c) v0 = fma(-sm.S[a][c], sm.S[a][j], v0);
-      }
-      const double v = v0 + v1;
-      const double piv = __shfl_sync(0xffffffffu, v, c);
-      const bool bad = !(piv > tiny) || !(piv < 1e300);
-      const double rinv = bad ? 0.0 : pcm_rsqrt(piv);
-      if (j == c) {
-        sm.drop[c] = bad;
-        sm.S[c][c] = bad ? 1.0 : piv * rinv;   // sqrt(piv)
-        sm.lam[c] = rinv;
-      } else if (j > c && j < k) {
-        sm.S[c][j] = v * rinv;
+        const double x = vc * inv_dmax;                  // in (1e-26, ~1]: safe for the FP32 seed
+        const bool bad = !(x > 1e-26) || !(x < 1e30);
+        double r = (double)rsqrtf((float)x);
+        r = r * fma(-0.5 * x, r * r, 1.5);
+        if (newton > 1) r = r * fma(-0.5 * x, r * r, 1.5);
+        const double rinv = bad ? 0.0 : r * rs_dmax;
+        if (j == c) {
+          sm.drop[c] = bad;
+          sm.S[c][c] = bad ? 1.0 : vc * rinv;   // sqrt(pivot)
+          sm.lam[c] = rinv;
+        } else {
+          sm.S[c][j] = vj * rinv;
+        }
       }
       __syncwarp();
     }
@@ -415,11 +423,41 @@ __device__ __forceinline__ void pcm_small_gram(PcmSmall& sm, const double* A, co
   __syncthreads();
 }
 
+// sum_c part[c * stride] over the nbp partial slots (nbp = CTA count rounded up to 8, <= 64; the
+// pad slots hold zeros) in CTA order.  All loads are issued before the first add, so the sum
+// costs one L2 round trip instead of one per unrolled batch.
+__device__ __forceinline__ double pcm_sum_partials(const double* __restrict__ part, size_t stride, int nbp) {
+  double v[8][8];
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    if (ch * 8 < nbp) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[ch][u] = part[(size_t)(ch * 8 + u) * stride];
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    if (ch * 8 < nbp) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[ch][u];
+    }
+  }
+  return s;
+}
+
 __global__ void __launch_bounds__(128)
     pcm_prep_kernel(const double* __restrict__ S0, int d, int k, int KP, int DP, double* __restrict__ Y0,
-                    double* __restrict__ Spart) {
+                    double* __restrict__ Spart, double* __restrict__ SpartB, int nbp) {
   __shared__ double ys[kPcmRows][kPcMaxK];
   const int row0 = blockIdx.x * kPcmRows;
+  if (blockIdx.x == 0) {   // zero the pad slots [gridDim.x, nbp) of both partial buffers
+    const int n = (nbp - (int)gridDim.x) * KP * KP;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      Spart[(size_t)gridDim.x * KP * KP + i] = 0.0;
+      SpartB[(size_t)gridDim.x * KP * KP + i] = 0.0;
+    }
+  }
   for (int i = threadIdx.x; i < kPcmRows * KP; i += blockDim.x) {
     const int r = i / KP, c = i - r * KP, row = row0 + r;
     const double v = (row < d && c < k) ? S0[(size_t)row * k + c] : 0.0;
@@ -440,8 +478,12 @@ template <int KMAX>
 __global__ void __launch_bounds__(kPcmThreads)
     pcm_iter_kernel(const float* __restrict__ G, int d, int k, int KP, int DP, int nb,
                     const double* __restrict__ Yprev, double* __restrict__ Ynext, double* __restrict__ Qout,
-                    const double* __restrict__ SpartIn, double* __restrict__ SpartOut, int passes, int last) {
+                    const double* __restrict__ SpartIn, double* __restrict__ SpartOut, int passes, int last,
+                    long long* __restrict__ tlog) {
   extern __shared__ __align__(16) unsigned char pcm_smem[];
+  int tl = 0;
+#define PCM_MARK() do { if (tlog && blockIdx.x == 0 && threadIdx.x == 0) tlog[tl++] = clock64(); } while (0)
+  PCM_MARK();
   PcmSmall& sm = *reinterpret_cast<PcmSmall*>(pcm_smem);
   double* Qt = reinterpret_cast<double*>(pcm_smem + ((sizeof(PcmSmall) + 15) & ~(size_t)15));   // [KP][DP]
   double* red = Qt + (size_t)KP * DP;                                // [JS][kPcmRows][KP]
@@ -452,35 +494,49 @@ __global__ void __launch_bounds__(kPcmThreads)
   float* Gs = reinterpret_cast<float*>(ys + kPcmRows * KP);          // [kPcmRows][d]
   const int row0 = blockIdx.x * kPcmRows;
 
-  // G rows of this CTA -> shared memory (coalesced; independent of the previous kernel's output)
+  // Programmatic dependent launch: let the next kernel of the chain start its own prologue now,
+  // stage this CTA's G rows (independent of the previous kernel), and only then wait for the
+  // previous kernel's Y / partials to be complete and visible.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int i = threadIdx.x; i < kPcmRows * d; i += kPcmThreads) {
     const int r = i / d, row = row0 + r;
     Gs[i] = row < d ? __ldg(G + (size_t)row * d + (i - r * d)) : 0.f;
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // S = sum of the per-CTA partials, CTA order
   for (int p = threadIdx.x; p < k * k; p += kPcmThreads) {
     const int a = p / k, b = p - a * k;
-    const double* src = SpartIn + a * KP + b;
-    double s = 0.0;
-    for (int c = 0; c < nb; ++c) s += src[(size_t)c * KP * KP];
-    sm.S[a][b] = s;
+    sm.S[a][b] = pcm_sum_partials(SpartIn + a * KP + b, (size_t)KP * KP, (nb + 7) & ~7);
   }
-  __syncthreads();
-  pcm_cholesky(sm, k);
-  // Q = Y R^-1 for all rows (redundantly in every CTA), column-major in shared memory
-  for (int row = threadIdx.x; row < DP; row += kPcmThreads) {
-    double q[KMAX];
+  // this thread's row of Y (loaded before the factorisation so that its latency hides behind it)
+  const int myrow = threadIdx.x;
+  double q[KMAX];
 #pragma unroll
-    for (int c = 0; c < KMAX; ++c) q[c] = (c < k && row < d) ? Yprev[(size_t)c * DP + row] : 0.0;
+  for (int c = 0; c < KMAX; ++c) q[c] = (c < k && myrow < d) ? Yprev[(size_t)c * DP + myrow] : 0.0;
+  __syncthreads();
+  PCM_MARK();
+  pcm_cholesky(sm, k, last ? 2 : 1);
+  PCM_MARK();
+  // Q = Y R^-1 for all rows (redundantly in every CTA), column-major in shared memory
+  if (myrow < DP) {
     pcm_solve_row<KMAX>(sm, q, k);
 #pragma unroll
     for (int c = 0; c < KMAX; ++c)
-      if (c < KP) Qt[(size_t)c * DP + row] = q[c];
+      if (c < KP) Qt[(size_t)c * DP + myrow] = q[c];
+  }
+  for (int row = myrow + kPcmThreads; row < DP; row += kPcmThreads) {   // d > 320 only
+    double q2[KMAX];
+#pragma unroll
+    for (int c = 0; c < KMAX; ++c) q2[c] = (c < k && row < d) ? Yprev[(size_t)c * DP + row] : 0.0;
+    pcm_solve_row<KMAX>(sm, q2, k);
+#pragma unroll
+    for (int c = 0; c < KMAX; ++c)
+      if (c < KP) Qt[(size_t)c * DP + row] = q2[c];
   }
   __syncthreads();
   for (int pass = 1; pass < passes; ++pass) {   // CholeskyQR2
     pcm_small_gram(sm, Qt, Qt, d, k, DP, true);
-    pcm_cholesky(sm, k);
+    pcm_cholesky(sm, k, 2);
     for (int row = threadIdx.x; row < d; row += kPcmThreads) {
       double q[KMAX];
 #pragma unroll
@@ -492,6 +548,7 @@ __global__ void __launch_bounds__(kPcmThreads)
     }
     __syncthreads();
   }
+  PCM_MARK();
   // Y rows of this CTA: tile = (row, 4 columns), j split over JS thread groups
   {
     const int t = threadIdx.x;
@@ -516,6 +573,7 @@ __global__ void __launch_bounds__(kPcmThreads)
     }
   }
   __syncthreads();
+  PCM_MARK();
   for (int i = threadIdx.x; i < kPcmRows * KP; i += kPcmThreads) {
     const int r = i / KP, c = i - r * KP, row = row0 + r;
     double s = 0.0;
@@ -540,6 +598,8 @@ __global__ void __launch_bounds__(kPcmThreads)
     }
     SpartOut[(size_t)blockIdx.x * KP * KP + a * KP + b] = s;
   }
+  PCM_MARK();
+#undef PCM_MARK
 }
 
 // Symmetric eigenproblem of sm.S (k <= 32), all warps of the CTA: Jacobi with the round-robin
@@ -635,21 +695,94 @@ __device__ __forceinline__ void pcm_jacobi(PcmSmall& sm, int k) {
   __syncthreads();
 }
 
+// npc == 1 fast path: the top eigenvector of sm.S (symmetric positive semi-definite, k x k)
+// without a full eigen-decomposition.  B = S / tr(S) is squared six times (B^64, renormalised
+// by its trace each time), which is numerically rank one whenever lambda_2 / lambda_1 < ~0.55;
+// its dominant column is polished by three power steps with S itself and accepted only if
+// || S v - lambda v || <= 1e-13 lambda.  Otherwise (no spectral gap) the caller falls back to
+// the Jacobi solver, so the result never depends on the gap assumption.  On success
+// sm.Vv[:, 0] = v and sm.order[0] = 0.  Returns the acceptance flag (uniform over the CTA).
+__device__ __forceinline__ bool pcm_top1(PcmSmall& sm, int k) {
+  const int t = threadIdx.x;
+  const int i = t / k, j = t - i * k;
+  const bool mine = t < k * k;
+  double tr = 0.0;
+  for (int a = 0; a < k; ++a) tr += sm.S[a][a];
+  const bool ok_tr = tr > 0.0 && tr < 1e300;
+  double rtr = ok_tr ? pcm_rcp(tr) : 0.0;
+  if (mine) sm.Vv[i][j] = sm.S[i][j] * rtr;
+  __syncthreads();
+  for (int m = 0; m < 6; ++m) {
+    double acc = 0.0;
+    if (mine)
+      for (int l = 0; l < k; ++l) acc = fma(sm.Vv[i][l], sm.Vv[l][j], acc);
+    if (mine) sm.P[i][j] = acc;
+    __syncthreads();
+    double tr2 = 0.0;
+    for (int a = 0; a < k; ++a) tr2 += sm.P[a][a];
+    rtr = tr2 > 0.0 ? pcm_rcp(tr2) : 0.0;
+    if (mine) sm.Vv[i][j] = acc * rtr;
+    __syncthreads();
+  }
+  bool ok = ok_tr;
+  if (t < 32) {
+    // dominant column = the one with the largest diagonal entry (first on ties)
+    double best = -1.0;
+    int arg = 0;
+    for (int a = 0; a < k; ++a) {
+      const double v = sm.Vv[a][a];
+      if (v > best) { best = v; arg = a; }
+    }
+    double v = t < k ? sm.Vv[t][arg] : 0.0;
+    double n2 = warp_sum(v * v);
+    v *= (n2 > 0.0) ? pcm_rsqrt(n2) : 0.0;
+    double lam = 0.0, res = 0.0;
+    for (int step = 0; step < 4; ++step) {   // three power steps with S, then the residual
+      if (t < k) sm.P[0][t] = v;
+      __syncwarp();
+      double y = 0.0;
+      if (t < k)
+        for (int a = 0; a < k; ++a) y = fma(sm.S[t][a], sm.P[0][a], y);
+      __syncwarp();
+      lam = warp_sum(y * v);
+      if (step == 3) {
+        const double r = y - lam * v;
+        res = warp_sum(r * r);
+        break;
+      }
+      n2 = warp_sum(y * y);
+      v = y * ((n2 > 0.0) ? pcm_rsqrt(n2) : 0.0);
+    }
+    const bool good = ok && lam > 0.0 && res <= 1e-26 * lam * lam;
+    if (t < k) sm.P[1][t] = v;
+    if (t == 0) sm.flag = good ? 1 : 0;
+  }
+  __syncthreads();
+  ok = sm.flag != 0;
+  if (ok) {
+    if (t < k) sm.Vv[t][0] = sm.P[1][t];
+    if (t == 0) sm.order[0] = 0;
+  }
+  __syncthreads();
+  return ok;
+}
+
 template <int KMAX>
 __global__ void __launch_bounds__(kPcmThreads)
     pcm_final_kernel(int d, int k, int KP, int DP, int nb, int npc, int transposed,
                      const double* __restrict__ Y, const double* __restrict__ Q,
-                     const double* __restrict__ Tpart, float* __restrict__ pc) {
+                     const double* __restrict__ Tpart, float* __restrict__ pc, long long* __restrict__ tlog) {
   extern __shared__ __align__(16) unsigned char pcm_smem[];
+  int tl = 0;
+#define PCM_MARK() do { if (tlog && threadIdx.x == 0) tlog[tl++] = clock64(); } while (0)
+  PCM_MARK();
   PcmSmall& sm = *reinterpret_cast<PcmSmall*>(pcm_smem);
   double* Wt = reinterpret_cast<double*>(pcm_smem + ((sizeof(PcmSmall) + 15) & ~(size_t)15));   // [KP][DP]
   double* cvec = Wt + (size_t)KP * DP;                                                            // [DP]
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int p = threadIdx.x; p < k * k; p += kPcmThreads) {
     const int a = p / k, b = p - a * k;
-    const double* src = Tpart + a * KP + b;
-    double s = 0.0;
-    for (int c = 0; c < nb; ++c) s += src[(size_t)c * KP * KP];
-    sm.S[a][b] = s;
+    sm.S[a][b] = pcm_sum_partials(Tpart + a * KP + b, (size_t)KP * KP, (nb + 7) & ~7);
   }
   __syncthreads();
   if (threadIdx.x < k) {   // symmetrise T = Q^T G Q
@@ -661,12 +794,13 @@ __global__ void __launch_bounds__(kPcmThreads)
     }
   }
   __syncthreads();
+  PCM_MARK();
   if (transposed) {      // Rayleigh-Ritz vectors of G on span(Q)
     for (int i = threadIdx.x; i < KP * DP; i += kPcmThreads) Wt[i] = Q[i];
     __syncthreads();
-    pcm_jacobi(sm, k);
+    if (!(npc == 1 && k * k <= kPcmThreads && pcm_top1(sm, k))) pcm_jacobi(sm, k);
   } else {               // left singular vectors of W = Y R^-1, T = R^T R
-    pcm_cholesky(sm, k);
+    pcm_cholesky(sm, k, 2);
     for (int row = threadIdx.x; row < DP; row += kPcmThreads) {
       double q[KMAX];
 #pragma unroll
@@ -677,9 +811,12 @@ __global__ void __launch_bounds__(kPcmThreads)
         if (c < KP) Wt[(size_t)c * DP + row] = q[c];
     }
     __syncthreads();
+    PCM_MARK();
     pcm_small_gram(sm, Wt, Wt, d, k, DP, true);
-    pcm_jacobi(sm, k);
+    PCM_MARK();
+    if (!(npc == 1 && k * k <= kPcmThreads && pcm_top1(sm, k))) pcm_jacobi(sm, k);
   }
+  PCM_MARK();
   for (int c = 0; c < npc; ++c) {
     const int sel = sm.order[c];
     for (int row = threadIdx.x; row < d; row += kPcmThreads) {
@@ -710,6 +847,8 @@ __global__ void __launch_bounds__(kPcmThreads)
     for (int row = threadIdx.x; row < d; row += kPcmThreads) pc[(size_t)c * d + row] = (float)(cvec[row] * sm.red[0]);
     __syncthreads();
   }
+  PCM_MARK();
+#undef PCM_MARK
 }
 
 struct PcmPlan {
@@ -719,17 +858,17 @@ struct PcmPlan {
 static PcmPlan pcm_plan(int d, int k) {
   PcmPlan P;
   P.KP = (k + 3) & ~3;
-  P.DP = (d + 7) & ~7;
+  P.DP = ((d + 7) & ~7) | 1;   // odd: the 4-column groups of one row land in different banks
   P.nb = (d + kPcmRows - 1) / kPcmRows;
   const int items = kPcmRows * (P.KP / 4);
   P.JS = kPcmThreads / items;
   P.blk = (size_t)P.KP * P.DP;              // doubles per d x k block
-  P.spart = (size_t)P.nb * P.KP * P.KP;     // doubles per partial buffer
+  P.spart = (size_t)((P.nb + 7) & ~7) * P.KP * P.KP;     // doubles per partial buffer (padded to 8 slots)
   const size_t small = (sizeof(PcmSmall) + 15) & ~(size_t)15;
   P.smem_iter = small + (P.blk + (size_t)(P.JS > 0 ? P.JS : 1) * kPcmRows * P.KP + kPcmRows * P.KP) * sizeof(double) +
                 (size_t)kPcmRows * d * sizeof(float);
   P.smem_final = small + (P.blk + P.DP) * sizeof(double);
-  P.ws_bytes = (3 * P.blk + 2 * P.spart) * sizeof(double);
+  P.ws_bytes = (3 * P.blk + 2 * P.spart) * sizeof(double) + 4096;   // + clock log (MMB_PC_TIMING)
   return P;
 }
 
@@ -740,25 +879,43 @@ static int pcm_run(const float* G, int d, const double* S0, int k, int npc, int 
   double* Yb[2] = {ws, ws + P.blk};
   double* Qg = ws + 2 * P.blk;
   double* Sp[2] = {ws + 3 * P.blk, ws + 3 * P.blk + P.spart};
+  // MMB_PC_TIMING=1: thread 0 of CTA 0 logs clock64() at phase boundaries (16 slots per kernel)
+  static const bool timing = getenv("MMB_PC_TIMING") && atoi(getenv("MMB_PC_TIMING")) != 0;
+  long long* tlog = timing ? (long long*)(ws + 3 * P.blk + 2 * P.spart) : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     MMB_CUDA(cudaFuncSetAttribute(pcm_iter_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MMB_CUDA(cudaFuncSetAttribute(pcm_final_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  pcm_prep_kernel<<<P.nb, 128, 0, st>>>(S0, d, k, P.KP, P.DP, Yb[0], Sp[0]);
+  pcm_prep_kernel<<<P.nb, 128, 0, st>>>(S0, d, k, P.KP, P.DP, Yb[0], Sp[0], Sp[1], (P.nb + 7) & ~7);
   MMB_LAUNCH_CHECK("pcm_prep");
+  // The iteration and final kernels are launched with programmatic stream serialisation: each
+  // may begin (prologue only) while its predecessor is still running and synchronises with
+  // griddepcontrol.wait before touching the predecessor's output.
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   for (int it = 0; it <= n_iter; ++it) {
     const int cur = it & 1;
-    pcm_iter_kernel<KMAX><<<P.nb, kPcmThreads, P.smem_iter, st>>>(G, d, k, P.KP, P.DP, P.nb, Yb[cur], Yb[cur ^ 1], Qg,
-                                                                  Sp[cur], Sp[cur ^ 1], it == n_iter ? 2 : 1,
-                                                                  it == n_iter ? 1 : 0);
-    MMB_LAUNCH_CHECK("pcm_iter");
+    cfg.gridDim = dim3(P.nb);
+    cfg.blockDim = dim3(kPcmThreads);
+    cfg.dynamicSmemBytes = P.smem_iter;
+    MMB_CUDA(cudaLaunchKernelEx(&cfg, pcm_iter_kernel<KMAX>, G, d, k, P.KP, P.DP, P.nb, (const double*)Yb[cur],
+                                Yb[cur ^ 1], Qg, (const double*)Sp[cur], Sp[cur ^ 1], it == n_iter ? 2 : 1,
+                                it == n_iter ? 1 : 0, tlog ? tlog + 16 * (it < 8 ? it : 8) : (long long*)nullptr));
   }
   const int fin = (n_iter + 1) & 1;
-  pcm_final_kernel<KMAX><<<1, kPcmThreads, P.smem_final, st>>>(d, k, P.KP, P.DP, P.nb, npc, transposed, Yb[fin], Qg,
-                                                              Sp[fin], pc);
-  MMB_LAUNCH_CHECK("pcm_final");
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(kPcmThreads);
+  cfg.dynamicSmemBytes = P.smem_final;
+  MMB_CUDA(cudaLaunchKernelEx(&cfg, pcm_final_kernel<KMAX>, d, k, P.KP, P.DP, P.nb, npc, transposed,
+                              (const double*)Yb[fin], (const double*)Qg, (const double*)Sp[fin], pc,
+                              tlog ? tlog + 16 * 10 : (long long*)nullptr));
   return MMB_OK;
 }
 
@@ -794,7 +951,7 @@ extern "C" int mmb_pc_from_gram(const float* G, int d, const double* S0, int k, 
   // grid-parallel chain of small kernels (default); MMB_PC_SOLVER=0 selects the one-CTA kernel
   static const bool one_cta = getenv("MMB_PC_SOLVER") && atoi(getenv("MMB_PC_SOLVER")) == 0;
   const PcmPlan P = pcm_plan(d, k);
-  if (!one_cta && P.JS >= 1 && P.smem_iter <= 200 * 1024 && P.smem_final <= 200 * 1024) {
+  if (!one_cta && P.JS >= 1 && P.nb <= 64 && P.smem_iter <= 200 * 1024 && P.smem_final <= 200 * 1024) {
     return k <= 16 ? pcm_run<16>(G, d, S0, k, npc, transposed, n_iter, pc, (double*)ws, as_stream(stream))
                    : pcm_run<32>(G, d, S0, k, npc, transposed, n_iter, pc, (double*)ws, as_stream(stream));
   }

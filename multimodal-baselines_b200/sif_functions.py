@@ -104,6 +104,22 @@ def start_block(n_rows, npc, seed=0):
     return np.random.RandomState(seed).normal(size=(int(n_rows), int(npc) + 10))
 
 
+_START_BLOCK_CACHE = {}
+
+
+def start_block_device(n_rows, npc, device):
+    """``start_block`` as a float64 CUDA tensor, cached per (rows, npc, device): it is a constant
+    of the algorithm (sklearn's ``random_state=0``), so it is generated and uploaded once."""
+    key = (int(n_rows), int(npc), str(device))
+    t = _START_BLOCK_CACHE.get(key)
+    if t is None:
+        if len(_START_BLOCK_CACHE) > 64:
+            _START_BLOCK_CACHE.clear()
+        t = torch.as_tensor(start_block(n_rows, npc)).to(device)
+        _START_BLOCK_CACHE[key] = t
+    return t
+
+
 def gram(X_t, mode=nv.GRAM_AUTO, return_ws=False):
     """``G = X^T X`` (d, d) float32 on the device (first half of compute_pc)."""
     n, d = X_t.shape
@@ -125,12 +141,12 @@ def pc_from_gram(G_t, npc, n_rows, X_t=None, S0_t=None, n_iter=7):
     transposed = n_rows < d
     if S0_t is None:
         if transposed:
-            omega = torch.as_tensor(start_block(n_rows, npc)).to(dev)
+            omega = start_block_device(n_rows, npc, dev)
             S0_t = torch.empty((d, k), dtype=torch.float64, device=dev)
             nv.check(lib.mmb_start_block_xt(nv.ptr(X_t), n_rows, d, nv.ptr(omega), k, nv.ptr(S0_t),
                                             nv.stream_ptr()))
         else:
-            S0_t = torch.as_tensor(start_block(d, npc)).to(dev)
+            S0_t = start_block_device(d, npc, dev)
     pc = torch.empty((npc, d), dtype=torch.float32, device=dev)
     nbytes = lib.mmb_pc_workspace_bytes(d, k)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -204,7 +220,7 @@ def sif_embedding_device(table_t, vocab_w_t, ids_t, npc=1, gram_mode=nv.GRAM_AUT
     st = _status(dev)
     pc = torch.empty((max(npc, 1), d), dtype=torch.float32, device=dev)
     if npc > 0 and omega_t is None:
-        omega_t = torch.as_tensor(start_block(d if n >= d else n, npc)).to(dev)
+        omega_t = start_block_device(d if n >= d else n, npc, dev)
     nbytes = lib.mmb_sif_workspace_bytes(n, d, npc)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     nv.check(lib.mmb_sif_embedding(nv.ptr(table_t), V, d, nv.ptr(vocab_w_t), nv.ptr(ids_t), n, L, npc,
