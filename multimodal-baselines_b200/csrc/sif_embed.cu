@@ -104,11 +104,13 @@ template <> struct RowOff<true> { typedef unsigned long long type; };
 // Accumulate tokens [base, base+32) of utterance i (lane = token) into acc; returns the
 // number of non-zero weights among them.
 //
-// Runs of equal adjacent ids are merged first: sum_j w_j * row == (sum_j w_j) * row, so a run
-// costs one row read instead of its length.  Right-padded batches end in a long run of the pad
-// id (37 % of the tokens of the bench workload, 73 % of the POM fixtures), which the reference
-// dutifully gathers and adds one by one (pad id 0 is an ordinary row with weight 1.0 in the POM
-// weights).  The divisor still counts every token's own weight.
+// Tokens of the chunk that name the same row are merged first (warp match.any):
+// sum_j w_j * row == (sum_j w_j) * row, so a row is read once per 32-token chunk however often
+// it occurs.  Right-padded batches end in a long run of the pad id (37 % of the tokens of the
+// bench workload, 73 % of the POM fixtures), which the reference dutifully gathers and adds one
+// by one (pad id 0 is an ordinary row with weight 1.0 in the POM weights), and natural text
+// repeats its most frequent words (Zipf: ~18 % of the non-pad tokens of a 32-token chunk).
+// The divisor still counts every token's own weight.
 template <int NCH, bool EXPLICIT_W, int UNROLL, bool WIDE>
 __device__ __forceinline__ int accumulate_chunk(RowAcc<NCH>& acc, const char* __restrict__ lane_base,
                                                 int V, unsigned row_bytes, bool tail,
@@ -132,13 +134,13 @@ __device__ __forceinline__ int accumulate_chunk(RowAcc<NCH>& acc, const char* __
   }
   const off_t off = (off_t)(row < 0 ? 0 : row) * row_bytes;
   const int cnt = __popc(__ballot_sync(0xffffffffu, w != 0.f));
-  // run heads: first lane of every maximal run of equal rows
-  const int prev = __shfl_up_sync(0xffffffffu, row, 1);
-  const bool head = (row >= 0) && (lane == 0 || row != prev);
+  // group heads: lowest lane of every set of lanes that hold the same row
+  const unsigned grp = __match_any_sync(0xffffffffu, row);
+  const bool head = (row >= 0) && (lane == __ffs(grp) - 1);
   const unsigned valid = __ballot_sync(0xffffffffu, row >= 0);
   unsigned heads = __ballot_sync(0xffffffffu, head);
   if (heads == 0xffffffffu) {
-    // common case (32 distinct neighbours): fixed shuffle lanes, no bit scanning
+    // common case (32 distinct rows): fixed shuffle lanes, no bit scanning
 #pragma unroll
     for (int j0 = 0; j0 < 32; j0 += UNROLL) {
       float wj[UNROLL];
@@ -155,14 +157,15 @@ __device__ __forceinline__ int accumulate_chunk(RowAcc<NCH>& acc, const char* __
     return cnt;
   }
   if (heads != valid) {
-    // segmented sum of the weights of each run into its head lane; a run ends where the next
-    // run (or an empty lane) starts
-    const unsigned breaks = (heads | ~valid) & ~((2u << lane) - 1u);   // run starts / gaps above me
-    const int run_end = breaks ? (__ffs(breaks) - 2) : 31;   // last lane of my run
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const float up = __shfl_down_sync(0xffffffffu, w, o);
-      if (lane + o <= run_end) w += up;
+    // sum the weights of every group with two or more members into its head lane (fixed
+    // butterfly order -> deterministic); singletons keep their own weight
+    unsigned multi = __ballot_sync(0xffffffffu, head && (grp & (grp - 1u)));
+    while (multi) {
+      const int j = __ffs(multi) - 1;
+      multi &= multi - 1u;
+      const unsigned gj = __shfl_sync(0xffffffffu, grp, j);
+      const float c = warp_sum(((gj >> lane) & 1u) ? w : 0.f);
+      if (lane == j) w = c;
     }
   }
   // walk the heads, UNROLL rows in flight per lane

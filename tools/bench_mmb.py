@@ -1,0 +1,175 @@
+"""Secondary metric: utterance-steps/s of ONE MMB2 latent-optimisation step
+(heads -> word term + 6 masked Gaussian terms -> backward -> SGD step) at the MOSI and POM
+shapes, through this repo's drop-in modules (libmmb_b200.so) against the reference's formulas
+evaluated by stock PyTorch ops -- on the same B200 ("library bar") and on the host CPU cores.
+
+    python tools/bench_mmb.py [--steps 50] [--shape mosi|pom|both] [--no-cpu]
+
+The stock-PyTorch arm restates reference losses.py:13-34 / 68-95 and models.py:187-202 (the
+CosineSimilarity broadcast over the whole vocabulary included); it is a baseline, not a checker
+(parity is tests/test_mmb_gpu.py against the oracle and the golden vectors).
+Prints one JSON line per shape.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'multimodal-baselines_b200'))
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+SHAPES = {
+    # name: (N, T, V, audio_dim, visual_dim)   (+2 positional columns as in make_configs.py:28)
+    'mosi': (1284, 20, 3016, 74 + 2, 47 + 2),
+    'pom': (600, 200, 7763, 43 + 2, 43 + 2),
+}
+D, B, A_SIF = 300, 64, 1e-3
+
+
+def synth(name, device, seed=0):
+    N, T, V, Ad, Vd = SHAPES[name]
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    table = 0.4 * torch.randn(V, D, generator=g) + 0.3 * torch.randn(1, D, generator=g)
+    ids = torch.randint(1, V, (N, T), generator=g)
+    lens = torch.randint(1, T + 1, (N, 1), generator=g)
+    pad = torch.arange(T)[None, :] >= lens
+    ids[pad] = 0
+    text = table[ids]
+    text_m = (~pad).float()[:, :, None].expand(N, T, D).contiguous()
+    aud = torch.rand(N, T, Ad, generator=g) * 2 - 1
+    vis = torch.rand(N, T, Vd, generator=g) * 2 - 1
+    aud[pad] = -10.
+    vis[pad] = -10.
+    aud_m = (~pad).float()[:, :, None].expand(N, T, Ad).contiguous()
+    vis_m = (~pad).float()[:, :, None].expand(N, T, Vd).contiguous()
+    text_w = torch.rand(N, T, generator=g) * 0.9 + 0.1
+    latents = (text * text_w[:, :, None]).sum(1) / T
+    to = lambda t: t.to(device)
+    return dict(table=to(table), text=to(text), text_m=to(text_m), aud=to(aud), aud_m=to(aud_m), vis=to(vis),
+                vis_m=to(vis_m), text_w=to(text_w), latents=to(latents), dims=(Ad, Vd), N=N)
+
+
+# ------------------------------------------------------------------ stock PyTorch restatement
+def torch_gauss(mu, sigma, x, m):
+    lp = torch.log(1. / torch.sqrt(2 * math.pi * sigma ** 2)) - (x - mu) ** 2 / (2 * sigma ** 2)
+    return (lp * m).sum(-1).sum(-1)
+
+
+def torch_word(e, table, w, sent, mask, a):
+    cos = nn.CosineSimilarity(dim=-1)
+    Z = (1. - torch.acos(cos(e.unsqueeze(1), table.unsqueeze(0))) / math.pi).sum(-1, keepdim=True)
+    alpha = 1. / (Z * a + 1.)
+    ctx = (1. - alpha) * (1. - torch.acos(cos(sent, e.unsqueeze(1))) / math.pi) / Z
+    return (torch.log(alpha * w + ctx) * mask[:, :, 0]).sum(-1)
+
+
+def torch_step(model, e, batch, table):
+    z = model.norm(e) if model.norm is not None else e
+    text, text_m, aud, aud_m, vis, vis_m, text_w = batch
+    data = {'audio': aud, 'visual': vis, 'audiovisual': torch.cat([aud, vis], -1),
+            'textaudio': torch.cat([text, aud], -1), 'textvisual': torch.cat([text, vis], -1),
+            'textaudiovisual': torch.cat([text, aud, vis], -1)}
+    masks = {'audio': aud_m, 'visual': vis_m, 'audiovisual': torch.cat([aud_m, vis_m], -1),
+             'textaudio': torch.cat([text_m, aud_m], -1), 'textvisual': torch.cat([text_m, vis_m], -1),
+             'textaudiovisual': torch.cat([text_m, aud_m, vis_m], -1)}
+    total = torch_word(e, table, text_w, text, text_m, A_SIF)
+    for mod, head in model.embed2out.items():
+        mu = head['mu'](z).unsqueeze(1)
+        sigma = head['log_sigma'](z).exp().unsqueeze(1)
+        total = total + torch_gauss(mu, sigma, data[mod], masks[mod])
+    return total
+
+
+# ------------------------------------------------------------------ this repo's path
+def ours_step(model, e, batch, word_fn, losses):
+    text, text_m, aud, aud_m, vis, vis_m, text_w = batch
+    C = losses.CatSegments
+    data = {'text': text, 'audio': aud, 'visual': vis, 'text_weights': text_w,
+            'audiovisual': C([aud, vis]), 'textaudio': C([text, aud]), 'textvisual': C([text, vis]),
+            'textaudiovisual': C([text, aud, vis])}
+    masks = {'text': text_m, 'audio': aud_m, 'visual': vis_m, 'audiovisual': C([aud_m, vis_m]),
+             'textaudio': C([text_m, aud_m]), 'textvisual': C([text_m, vis_m]),
+             'textaudiovisual': C([text_m, aud_m, vis_m])}
+    out = model(e)
+    return losses.get_log_prob_matrix({}, e, out, data, masks, word_fn, device=e.device)
+
+
+def run(name, steps, do_cpu):
+    import losses
+    import models
+    import simplesif
+    dev = torch.device('cuda')
+    S = synth(name, dev)
+    Ad, Vd = S['dims']
+    torch.manual_seed(0)
+    model = models.AudioVisualGeneratorMultimodal(D, Ad, Vd, norm='layer_norm', frozen_weights=False).to(dev)
+    word_fn = simplesif.make_word_log_prob_fn({'word_sim_metric': 'angular'}, None, S['table'], a=A_SIF)
+    n_batches = S['N'] // B
+    perm = torch.randperm(S['N'], generator=torch.Generator().manual_seed(1)).to(dev)
+
+    def make_loop(step_fn, device):
+        Sd = S if device.type == 'cuda' else {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in S.items()}
+        mdl = model if device.type == 'cuda' else \
+            models.AudioVisualGeneratorMultimodal(D, Ad, Vd, norm='layer_norm', frozen_weights=False)
+        lat = Sd['latents'].clone().requires_grad_(True)
+        opt = torch.optim.SGD([lat] + list(mdl.parameters()), lr=1e-7)  # tiny: synthetic data, timing only
+        pm = perm.to(device)
+
+        def one(i):
+            j = pm[(i % n_batches) * B:(i % n_batches + 1) * B]
+            batch = tuple(Sd[k][j] for k in ('text', 'text_m', 'aud', 'aud_m', 'vis', 'vis_m', 'text_w'))
+            opt.zero_grad()
+            lp = step_fn(mdl, lat[j], batch)
+            loss = (-lp).mean()
+            loss.backward()
+            opt.step()
+            return loss
+        return one
+
+    def time_gpu(one, n):
+        for i in range(5):
+            one(i)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(n):
+            loss = one(i)
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / n, float(loss)
+
+    ours = make_loop(lambda m, e, b: ours_step(m, e, b, word_fn, losses), dev)
+    ms_ours, l_ours = time_gpu(ours, steps)
+    stock = make_loop(lambda m, e, b: torch_step(m, e, b, S['table']), dev)
+    ms_stock, l_stock = time_gpu(stock, max(5, steps // 5))
+    res = {'metric': 'utterance-steps/s (one MMB2 fwd+bwd+SGD step, B=64)', 'shape': name,
+           'N_T_V_A_Vd': SHAPES[name], 'steps': steps,
+           'b200_fused': {'ms_per_step': ms_ours, 'value': B / ms_ours * 1e3, 'loss': l_ours},
+           'b200_stock_torch': {'ms_per_step': ms_stock, 'value': B / ms_stock * 1e3, 'loss': l_stock}}
+    if do_cpu:
+        cpu = make_loop(lambda m, e, b: torch_step(m, e, b, S['table'].cpu()), torch.device('cpu'))
+        cpu(0)
+        t0 = time.perf_counter()
+        n = 3
+        for i in range(n):
+            cpu(i)
+        dt = (time.perf_counter() - t0) / n
+        res['cpu_stock_torch'] = {'ms_per_step': dt * 1e3, 'value': B / dt, 'cores': torch.get_num_threads()}
+    print(json.dumps(res))
+    return res
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--shape', default='both')
+    ap.add_argument('--no-cpu', action='store_true')
+    a = ap.parse_args()
+    for nm in (['mosi', 'pom'] if a.shape == 'both' else [a.shape]):
+        run(nm, a.steps, not a.no_cpu)
