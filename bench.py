@@ -229,6 +229,7 @@ def main():
         run_reference_arm(args)
         return
 
+    os.environ.setdefault('NCCL_DEBUG', 'WARN')     # keep stdout to the one JSON line
     import torch.distributed as dist
     import _native as nv
     import sif_functions as sf
@@ -375,13 +376,15 @@ def main():
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'utterances': N_UTT, 'tokens_per_utterance': L_TOK, 'vocab': VOCAB,
                        'dim': DIM, 'ids': 'Zipf(1.1), lengths U[16,64], pad id 0', 'npc': 1,
-                       'parallelism': 'utterance shards x%d + 1 NCCL all-reduce of the 300x300 Gram' % world,
+                       'parallelism': 'utterance shards x%d + 1 all-reduce of the 300x300 Gram (%s)' % (
+                           world, 'NVLink peer memory, fused into the Gram reduce kernel' if (world > 1 and mdist.default_comm() is not None) else 'NCCL' if world > 1 else 'none at 1 GPU'),
                        'l2': 'inputs larger than L2 (ids %.1f GB + embeddings %.1f GB per rank, table 0.48 GB)'
                              % (n_local * L_TOK * 8 / 1e9, n_local * DIM * 4 / 1e9)},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': LAUNCHES_PER_STEP * args.steps,
             'roofline': roofline, 'cpu_baseline': cpu,
         }))
     if world > 1:
+        mdist.close_default_comms()
         dist.destroy_process_group()
 
 

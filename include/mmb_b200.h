@@ -48,7 +48,8 @@ enum {
 
 enum {
   MMB_STATUS_BAD_INDEX = 1, /* an id was outside [-V, V) (NumPy would raise IndexError) */
-  MMB_STATUS_NONFINITE = 2  /* a log-probability was +-inf/NaN (losses.py:258-264)      */
+  MMB_STATUS_NONFINITE = 2, /* a log-probability was +-inf/NaN (losses.py:258-264)      */
+  MMB_STATUS_COMM_TIMEOUT = 4 /* a peer never raised its flag in mmb_*_peer (rank died)   */
 };
 
 enum { /* mmb_gram `mode` */
@@ -132,6 +133,33 @@ MMB_API int mmb_sif_embedding_host(const float* table_dev, int64_t V, int d, con
                            const int64_t* x_host, int64_t N, int64_t L, int npc,
                            const double* Omega_host, void* emb_host, int emb_f64,
                            float* pc_host, int gram_mode, int64_t chunk_rows);
+
+/* ---------------------------------------------------------------- multi-GPU */
+/* The reference has no distributed code; utterances shard over the GPUs of one box and the only
+ * exchange is the sum of the per-rank Grams (and, for N < d, of the start blocks).  These entry
+ * points do that sum over NVLink peer memory inside the kernel that finishes the Gram, one
+ * process per GPU:
+ *   every rank allocates one exchange buffer (mmb_comm_alloc), exports its 64-byte CUDA IPC
+ *   handle (mmb_comm_export), the host side all-gathers the handles (torch.distributed), and
+ *   opens the peers' buffers (mmb_comm_open).  `bufs` is a HOST array of `world` device
+ *   pointers in rank order (bufs[rank] = the rank's own buffer); `epoch` is a counter > 0 that
+ *   every rank advances by one per call (same call sequence on all ranks); world <= 8.
+ * Sums are taken in rank order, so all ranks obtain identical bits.  A peer that never arrives
+ * sets MMB_STATUS_COMM_TIMEOUT in `status` after ~4 s instead of hanging.                    */
+MMB_API size_t mmb_comm_bytes(void);
+MMB_API int mmb_comm_alloc(void** buf);
+MMB_API int mmb_comm_free(void* buf);
+MMB_API int mmb_comm_export(void* buf, void* handle64);
+MMB_API int mmb_comm_open(const void* handle64, void** peer_buf);
+MMB_API int mmb_comm_close(void* peer_buf);
+/* x (n elements, float32 or float64 when is_f64 != 0; n * elem size <= 512 KiB) <- sum over ranks. */
+MMB_API int mmb_allreduce_peer(void* x, int64_t n, int is_f64, int rank, int world, void* const* bufs,
+                               uint64_t epoch, int* status, mmb_stream_t stream);
+/* mmb_gram followed by the all-reduce of G: on the tcgen05 path the cross-CTA reduction of the
+ * Gram partials and the cross-rank exchange are ONE kernel.  N may be 0 on a rank.           */
+MMB_API int mmb_gram_allreduce_peer(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_bytes,
+                                    int mode, int rank, int world, void* const* bufs, uint64_t epoch,
+                                    int* status, mmb_stream_t stream);
 
 /* ---------------------------------------------------------------- MMB (A6-A9) ----- */
 /* In this section the pointer tables (W, b, out, seg_val ...) are HOST arrays of DEVICE

@@ -31,6 +31,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "peer_comm.cuh"
 
 namespace mmb {
 
@@ -348,6 +349,42 @@ __global__ void __launch_bounds__(256)
   G[(size_t)j * kD + i] = s;
 }
 
+// The same second stage fused with the cross-rank exchange (multi-GPU): sum this rank's per-CTA
+// partials straight into its NVLink-visible exchange slot, raise the flags, wait for the peers and
+// add all ranks' Grams in rank order -- one launch, no library collective, identical bits on
+// every rank.  Launched with one thread per matrix element; the whole grid is co-resident
+// (352 CTAs x 256 threads), which the flag wait requires.
+__global__ void __launch_bounds__(256)
+    gram_tc_reduce_allreduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ G,
+                                    const PeerComm comm, int* __restrict__ status) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  float* mine = (float*)comm_slot(comm, comm.rank);
+  if (idx < kD * kD) {
+    const int j = idx / kD, i = idx % kD;
+    if (j >= i) {
+      const float* p;
+      if (i < 128) p = partial + (size_t)j * 128 + i;
+      else if (i < 256) p = partial + (size_t)(304 + (j - 128)) * 128 + (i - 128);
+      else p = partial + 128 * kColsAB + (size_t)(i - 256) * kColsC + (j - 256);
+      float s = 0.f;
+      for (int c = 0; c < n_cta; ++c) s += p[(size_t)c * kPartialStride];
+      mine[(size_t)i * kD + j] = s;
+      mine[(size_t)j * kD + i] = s;
+    }
+  }
+  __syncthreads();
+  comm_publish(comm);
+  if (!comm_wait(comm)) {
+    if (threadIdx.x == 0) atomicOr(status, MMB_STATUS_COMM_TIMEOUT);
+    return;
+  }
+  if (idx < kD * kD) {
+    float s = 0.f;
+    for (int r = 0; r < comm.world; ++r) s += *((const volatile float*)comm_slot(comm, r) + idx);
+    G[idx] = s;
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -389,7 +426,7 @@ size_t gram_tc_workspace_bytes(int64_t N, int d) {
   return (size_t)tc::plan(N) * tc::kPartialStride * sizeof(float);
 }
 
-int gram_tc(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_bytes, cudaStream_t st) {
+static int gram_tc_main(const float* X, int64_t N, int d, void* ws, size_t ws_bytes, cudaStream_t st, int* n_cta_out) {
   using namespace tc;
   MMB_REQUIRE(d == kD, "tcgen05 Gram is specialised for d == 300");
   MMB_REQUIRE(N < ((int64_t)1 << 31) - 64, "N too large for 32-bit TMA coordinates");
@@ -431,8 +468,30 @@ int gram_tc(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_byte
   prm.partial = (float*)ws;
   gram_tc_kernel<<<n_cta, kThreads, kSmemBytes, st>>>(tmap, prm);
   MMB_LAUNCH_CHECK("gram_tc");
+  *n_cta_out = n_cta;
+  return MMB_OK;
+}
+
+int gram_tc(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using namespace tc;
+  int n_cta = 0;
+  const int rc = gram_tc_main(X, N, d, ws, ws_bytes, st, &n_cta);
+  if (rc) return rc;
   gram_tc_reduce_kernel<<<(kD * kD + 255) / 256, 256, 0, st>>>((const float*)ws, n_cta, G);
   MMB_LAUNCH_CHECK("gram_tc_reduce");
+  return MMB_OK;
+}
+
+// Gram + all-reduce over peer memory in two launches: the tcgen05 kernel, then the partial
+// reduction fused with the NVLink exchange.
+int gram_tc_allreduce(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_bytes, const PeerComm& comm,
+                      int* status, cudaStream_t st) {
+  using namespace tc;
+  int n_cta = 0;
+  const int rc = gram_tc_main(X, N, d, ws, ws_bytes, st, &n_cta);
+  if (rc) return rc;
+  gram_tc_reduce_allreduce_kernel<<<(kD * kD + 255) / 256, 256, 0, st>>>((const float*)ws, n_cta, G, comm, status);
+  MMB_LAUNCH_CHECK("gram_tc_reduce_allreduce");
   return MMB_OK;
 }
 

@@ -12,9 +12,16 @@ the table and the vocabulary weights are replicated.  Per split of the data:
                  broadcast is needed
     rank-local:  emb_r -= (emb_r pc^T) pc
 
-Works with any torch.distributed backend: NCCL over NVLink on the GPUs; the partition /
-reduction arithmetic is also exercised with gloo on CPU in tests/test_dist_cpu.py.
+The exchange has two implementations:
+  * ``PeerComm`` (default on one box, world <= 8): libmmb_b200.so's own one-shot all-reduce over
+    NVLink peer memory (CUDA IPC buffers), fused into the kernel that finishes the Gram
+    (``mmb_gram_allreduce_peer``) -- ranks add in rank order, so every rank holds identical bits;
+  * ``torch.distributed.all_reduce`` (NCCL on GPUs, gloo on CPU): the fallback for any other
+    topology, and what tests/test_dist_cpu.py exercises for the partition / reduction arithmetic.
 """
+import ctypes as C
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -35,6 +42,116 @@ def allreduce_sum_(t, group=None):
     return t
 
 
+class PeerComm(object):
+    """NVLink exchange buffers of the ranks of one box (one process per GPU).
+
+    Every rank allocates one buffer in libmmb_b200.so, the 64-byte CUDA IPC handles travel
+    through ``torch.distributed.all_gather_object`` once, and each rank maps its peers' buffers.
+    ``epoch`` advances by one per collective call; all ranks must issue the same sequence."""
+
+    def __init__(self, group=None):
+        import _native as nv
+        self.nv, self.lib = nv, nv.lib
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError('PeerComm supports at most 8 ranks (one NVLink box)')
+        self.dev = torch.device('cuda', torch.cuda.current_device())
+        own = C.c_void_p()
+        nv.check(self.lib.mmb_comm_alloc(C.byref(own)))
+        self.own = own
+        handle = (C.c_char * 64)()
+        nv.check(self.lib.mmb_comm_export(own, handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (os.uname().nodename, bytes(handle.raw)), group=group)
+        if len(set(h[0] for h in handles)) != 1:
+            raise ValueError('PeerComm needs all ranks on one host')
+        self.opened = []
+        bufs = []
+        for r, (_, raw) in enumerate(handles):
+            if r == self.rank:
+                bufs.append(own.value)
+            else:
+                p = C.c_void_p()
+                nv.check(self.lib.mmb_comm_open(C.create_string_buffer(raw, 64), C.byref(p)))
+                self.opened.append(p)
+                bufs.append(p.value)
+        self.bufs = (C.c_void_p * self.world)(*bufs)
+        self.epoch = 0
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        dist.barrier(group=group)        # every rank has mapped every buffer before the first use
+
+    def _next(self):
+        self.epoch += 1
+        return C.c_uint64(self.epoch)
+
+    def allreduce_(self, t):
+        """In-place sum over ranks of a small float32 / float64 CUDA tensor (<= 512 KiB)."""
+        nv = self.nv
+        assert t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.float64)
+        nv.check(self.lib.mmb_allreduce_peer(nv.ptr(t), t.numel(), int(t.dtype == torch.float64), self.rank,
+                                             self.world, self.bufs, self._next(), nv.ptr(self.status),
+                                             nv.stream_ptr()))
+        return t
+
+    def gram_allreduce(self, emb, mode=0):
+        """G = sum over ranks of emb_r^T emb_r: local tcgen05 Gram, then ONE kernel that reduces
+        its partials and exchanges them over NVLink."""
+        nv = self.nv
+        n, d = emb.shape
+        G = torch.empty((d, d), dtype=torch.float32, device=emb.device)
+        nbytes = self.lib.mmb_gram_workspace_bytes(max(n, 1), d, mode)
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=emb.device)
+        nv.check(self.lib.mmb_gram_allreduce_peer(nv.ptr(emb), n, d, nv.ptr(G), nv.ptr(ws), nbytes, mode, self.rank,
+                                                  self.world, self.bufs, self._next(), nv.ptr(self.status),
+                                                  nv.stream_ptr()))
+        return G
+
+    def check(self):
+        """Synchronises; raises if a peer never arrived."""
+        if int(self.status.item()) & self.nv.STATUS_COMM_TIMEOUT:
+            raise self.nv.MMBError('peer all-reduce timed out: a rank never raised its flag')
+
+    def close(self):
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier(group=self.group)   # nobody is still reading this rank's buffer
+        for p in self.opened:
+            self.lib.mmb_comm_close(p)
+        self.opened = []
+        if self.own is not None:
+            self.lib.mmb_comm_free(self.own)
+            self.own = None
+
+
+_DEFAULT_COMM = {}
+
+
+def default_comm(group=None):
+    """The process-wide PeerComm of `group` (created on first use), or None when the exchange
+    should go through torch.distributed (no process group, one rank, non-NCCL backend, or
+    MMB_PEER_COMM=0)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
+        return None
+    if os.environ.get('MMB_PEER_COMM', '1') == '0' or dist.get_backend(group) != 'nccl':
+        return None
+    key = id(group)
+    if key not in _DEFAULT_COMM:
+        try:
+            _DEFAULT_COMM[key] = PeerComm(group)
+        except ValueError:
+            _DEFAULT_COMM[key] = None
+    return _DEFAULT_COMM[key]
+
+
+def close_default_comms():
+    for c in _DEFAULT_COMM.values():
+        if c is not None:
+            c.close()
+    _DEFAULT_COMM.clear()
+
+
 def local_start_block(emb_local, n_global, lo, npc, start_block_fn):
     """N_global < d: this rank's share of S0 = X^T Omega, using rows [lo, hi) of the global
     seeded Omega (float64, d x (npc+10)); the caller all-reduces it."""
@@ -43,7 +160,7 @@ def local_start_block(emb_local, n_global, lo, npc, start_block_fn):
 
 
 def sharded_sif_embedding(table_t, vocab_w_t, ids_local_t, n_global, lo, npc=1, group=None, gram_mode=0,
-                          timers=None):
+                          timers=None, comm='auto'):
     """SIF embedding + PC removal of this rank's block of a split of `n_global` utterances.
 
     table_t (V, d) f32, vocab_w_t (V,) f32, ids_local_t (n_local, L) int64 -- CUDA tensors on
@@ -65,16 +182,25 @@ def sharded_sif_embedding(table_t, vocab_w_t, ids_local_t, n_global, lo, npc=1, 
     mark('embed')
     if npc <= 0:
         return emb, None, st
-    if n_local > 0:
-        G = sf.gram(emb, gram_mode)
-    else:
-        G = torch.zeros((d, d), dtype=torch.float32, device=dev)
-    mark('gram')
-    allreduce_sum_(G, group)
+    if comm == 'auto':
+        comm = default_comm(group)
     S0 = None
-    if n_global < d:
-        S0 = local_start_block(emb, n_global, lo, npc, sf.start_block)
-        allreduce_sum_(S0, group)
+    if comm is not None:
+        # Gram partial reduction + NVLink exchange in one kernel ('gram' then covers both stages)
+        G = comm.gram_allreduce(emb, gram_mode)
+        mark('gram')
+        if n_global < d:
+            S0 = comm.allreduce_(local_start_block(emb, n_global, lo, npc, sf.start_block).contiguous())
+    else:
+        if n_local > 0:
+            G = sf.gram(emb, gram_mode)
+        else:
+            G = torch.zeros((d, d), dtype=torch.float32, device=dev)
+        mark('gram')
+        allreduce_sum_(G, group)
+        if n_global < d:
+            S0 = local_start_block(emb, n_global, lo, npc, sf.start_block)
+            allreduce_sum_(S0, group)
     mark('allreduce')
     pc = sf.pc_from_gram(G, npc, n_global, S0_t=S0)
     mark('pc')

@@ -31,6 +31,27 @@ def main():
         ids[torch.arange(L, device=dev)[None, :] >= lens] = 0
         lo, hi = sif_dist.shard_bounds(n_global, world, rank)
         emb_l, pc_l, st = sif_dist.sharded_sif_embedding(table, vw, ids[lo:hi].contiguous(), n_global, lo, npc=1)
+        # the NVLink peer exchange (default) against the NCCL all-reduce
+        emb_n, pc_n, _ = sif_dist.sharded_sif_embedding(table, vw, ids[lo:hi].contiguous(), n_global, lo, npc=1,
+                                                        comm=None)
+        comm = sif_dist.default_comm()
+        assert comm is not None, 'PeerComm was not created'
+        comm.check()
+        cos_n = float((pc_l[0].double() @ pc_n[0].double()))
+        err_n = float((emb_l - emb_n).abs().max() / emb_n.abs().max())
+        # stand-alone peer all-reduce == rank-ordered sum, bit for bit
+        x = torch.randn(90000, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + rank))
+        xs = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(xs, x)
+        want = xs[0].clone()
+        for r in range(1, world):
+            want += xs[r]
+        got = comm.allreduce_(x.clone())
+        comm.check()
+        exact = torch.equal(got, want)
+        print('rank %d N=%d: peer vs NCCL: pc cos %.8f, emb err %.2e; peer all-reduce exact %s'
+              % (rank, n_global, cos_n, err_n, exact), flush=True)
+        ok = ok and cos_n > 0.9999999 and err_n < 1e-6 and exact
         emb_1, pc_1 = sf.sif_embedding_device(table, vw, ids, npc=1, return_pc=True)
         cos = float((pc_l[0].double() @ pc_1[0].double()))
         err = float((emb_l - emb_1[lo:hi]).abs().max() / emb_1.abs().max())
@@ -43,6 +64,7 @@ def main():
               % (rank, n_global, cos, err, same, 'ok' if good else 'FAIL'), flush=True)
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
+    sif_dist.close_default_comms()
     dist.destroy_process_group()
     sys.exit(int(flag.item() != 0))
 
