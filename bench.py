@@ -190,7 +190,7 @@ def run_reference_arm(args):
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
-    }))
+    }), flush=True)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -229,7 +229,8 @@ def main():
         run_reference_arm(args)
         return
 
-    os.environ.setdefault('NCCL_DEBUG', 'WARN')     # keep stdout to the one JSON line
+    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'           # NCCL's version banner goes to stdout: keep it to the one JSON line
     import torch.distributed as dist
     import _native as nv
     import sif_functions as sf
@@ -382,7 +383,7 @@ def main():
                              % (n_local * L_TOK * 8 / 1e9, n_local * DIM * 4 / 1e9)},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': LAUNCHES_PER_STEP * args.steps,
             'roofline': roofline, 'cpu_baseline': cpu,
-        }))
+        }), flush=True)
     if world > 1:
         mdist.close_default_comms()
         dist.destroy_process_group()

@@ -114,12 +114,15 @@ class PeerComm(object):
             raise self.nv.MMBError('peer all-reduce timed out: a rank never raised its flag')
 
     def close(self):
+        """Unmap the peers' buffers, then (after a barrier) free this rank's own: CUDA requires that
+        every importer has closed its mapping before the exporter frees the allocation."""
         torch.cuda.synchronize()
-        if dist.is_initialized():
-            dist.barrier(group=self.group)   # nobody is still reading this rank's buffer
         for p in self.opened:
             self.lib.mmb_comm_close(p)
         self.opened = []
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+            torch.cuda.synchronize()
         if self.own is not None:
             self.lib.mmb_comm_free(self.own)
             self.own = None
