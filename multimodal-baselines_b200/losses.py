@@ -37,8 +37,24 @@ def _segments(values, mask):
 
 
 def _exit_if_nonfinite(status, names):
-    """reference losses.py:258-264: a non-finite log-probability prints and exits."""
+    """reference losses.py:258-264: a non-finite log-probability prints and exits.  With a status
+    sink installed (mmb_ops.set_status_sink, the graph-captured loop) the check is deferred to the
+    caller's next synchronisation point (check_status_sink)."""
+    if mmb_ops.status_deferred():
+        return
     if int(status.item()) & 2:
+        for n in names:
+            print(n, 'inf')
+        sys.exit()
+
+
+def check_status_sink(status, names=('log-probability',)):
+    """Read the deferred status word (synchronises), clear it, and abort like the reference
+    (print + sys.exit) if any step since the last check produced a non-finite log-probability."""
+    bits = int(status.item())
+    if bits:
+        status.zero_()
+    if bits & 2:
         for n in names:
             print(n, 'inf')
         sys.exit()

@@ -150,8 +150,7 @@ class WordLLFunction(torch.autograd.Function):
         if sent.shape[:2] != (B, L) or sent.shape[2] != d or mask.shape[:2] != (B, L):
             raise RuntimeError('word term: shapes do not match (latents %s, sent %s, weights %s, mask %s)'
                                % (tuple(e.shape), tuple(sent.shape), tuple(word_w.shape), tuple(mask.shape)))
-        inv_norm = torch.empty(V, dtype=torch.float32, device=e.device)
-        nv.check(lib.mmb_row_inv_norm(nv.ptr(table), V, d, nv.ptr(inv_norm), nv.stream_ptr()))
+        inv_norm = table_inv_norm(table)
         lp = torch.empty(B, dtype=torch.float32, device=e.device)
         grad = torch.empty_like(e)
         nbytes = lib.mmb_word_ll_workspace_bytes(B, V, d)
@@ -170,5 +169,40 @@ class WordLLFunction(torch.autograd.Function):
         return g.unsqueeze(1) * grad, None, None, None, None, None, None
 
 
+_STATUS_SINK = None
+_INV_NORM_CACHE = {}
+
+
+def set_status_sink(t):
+    """Route every kernel's status bits into ONE persistent device word `t` (int32, shape (1,))
+    instead of a fresh word per call, and stop the per-call host read-back: the caller checks
+    the sink when it next synchronises (once per epoch in the graph-captured loop).  ``None``
+    restores the per-call behaviour.  Returns the previous sink."""
+    global _STATUS_SINK
+    prev, _STATUS_SINK = _STATUS_SINK, t
+    return prev
+
+
+def status_deferred():
+    return _STATUS_SINK is not None
+
+
 def new_status(device):
+    if _STATUS_SINK is not None:
+        return _STATUS_SINK
     return torch.zeros(1, dtype=torch.int32, device=device)
+
+
+def table_inv_norm(table):
+    """1 / max(||row||, 1e-8) of the word table (torch CosineSimilarity's clamp), cached while the
+    same tensor version is passed again -- the table is a constant of the optimisation loop."""
+    key = (table.data_ptr(), tuple(table.shape), table._version, str(table.device))
+    hit = _INV_NORM_CACHE.get('k')
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    V, d = table.shape
+    inv_norm = torch.empty(V, dtype=torch.float32, device=table.device)
+    nv.check(lib.mmb_row_inv_norm(nv.ptr(table), V, d, nv.ptr(inv_norm), nv.stream_ptr()))
+    if not torch.cuda.is_current_stream_capturing():
+        _INV_NORM_CACHE['k'] = (key, inv_norm)
+    return inv_norm

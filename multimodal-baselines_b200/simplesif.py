@@ -94,6 +94,124 @@ def _warn_tiny_sigma(out):
         print({m: float(d['sigma'].min()) for m, d in out.items()}, "boo!")
 
 
+class GraphedStep(object):
+    """One latent-optimisation step -- gather the batch, generator heads, word + Gaussian
+    log-likelihoods, backward, optimizer step -- captured ONCE as a CUDA graph and replayed per
+    batch.  The step is a few dozen small launches at B = 64, so in the
+    eager loop Python, launch latency and the per-step status read-back dominate; the replay is
+    one launch with no host synchronisation (non-finite values are flagged in a device word that
+    the caller checks once per epoch).
+
+    The captured work is exactly what the eager loop of ``optimize_latents`` runs on the same
+    indices, so the results agree to rounding (tests/test_mmb_gpu.py)."""
+
+    def __init__(self, args, gen_model, embeddings, dataset, optimizer, word_prob_fn, device):
+        import mmb_ops
+        self.args, self.gen_model, self.embeddings = args, gen_model, embeddings
+        self.dataset, self.optimizer, self.word_prob_fn, self.device = dataset, optimizer, word_prob_fn, device
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self.graphs = {}
+        self.mmb_ops = mmb_ops
+
+    def _step(self, j):
+        x = self.dataset[j]                       # batched gather of the device-resident tensors
+        _, batch_data, batch_masks = _batch_dicts(self.args, x)
+        e = self.embeddings[j]
+        out = self.gen_model(e)
+        log_prob = -get_log_prob_matrix(self.args, e, out, batch_data, batch_masks, self.word_prob_fn,
+                                        device=self.device, verbose=False)
+        loss = log_prob.mean()
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    def _snapshot(self):
+        params = [p for g in self.optimizer.param_groups for p in g['params']]
+        saved = [p.detach().clone() for p in params]
+        bufs = [b.detach().clone() for b in self.gen_model.buffers()]
+        return params, saved, bufs
+
+    def _restore(self, params, saved, bufs):
+        with torch.no_grad():
+            for p, s in zip(params, saved):
+                p.copy_(s)
+            for b, s in zip(self.gen_model.buffers(), bufs):
+                b.copy_(s)
+            for st in self.optimizer.state.values():     # Adam moments / step counters back to zero
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+
+    def _capture(self, n):
+        """Warm up on a side stream (state restored afterwards), then capture a step for n rows."""
+        static_j = torch.zeros(n, dtype=torch.int64, device=self.device)
+        params, saved, bufs = self._snapshot()
+        had_state = len(self.optimizer.state) > 0
+        state_saved = None
+        if had_state:
+            state_saved = [{k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                           for st in self.optimizer.state.values()]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.optimizer.zero_grad(set_to_none=True)
+                self._step(static_j)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self._restore(params, saved, bufs)
+        self.status.zero_()                       # warm-up ran on dummy indices
+        if had_state:
+            with torch.no_grad():
+                for st, old in zip(self.optimizer.state.values(), state_saved):
+                    for k, v in old.items():
+                        if torch.is_tensor(v):
+                            st[k].copy_(v)
+        graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            static_loss = self._step(static_j)
+        # the capture itself does not execute; state is untouched
+        return graph, static_j, static_loss
+
+    def __call__(self, j):
+        """Run one step on the row indices j (int64 CUDA tensor); returns the (device) loss."""
+        prev = self.mmb_ops.set_status_sink(self.status)
+        try:
+            n = int(j.shape[0])
+            if n not in self.graphs:
+                self.graphs[n] = self._capture(n)
+            graph, static_j, static_loss = self.graphs[n]
+            static_j.copy_(j)
+            graph.replay()
+            return static_loss
+        finally:
+            self.mmb_ops.set_status_sink(prev)
+
+    def check(self):
+        from losses import check_status_sink
+        check_status_sink(self.status, list(self.gen_model.embed2out.keys()))
+
+
+def _epoch_index_batches(dataloader, device):
+    """The index batches the DataLoader would produce this epoch, drawing from the same RNG in
+    the same order (num_workers = 0: one base-seed draw when the iterator is built, then the
+    sampler's own draws), without collating the data sample by sample."""
+    torch.empty((), dtype=torch.int64).random_(generator=dataloader.generator)
+    for idx in dataloader.batch_sampler:
+        yield torch.as_tensor(idx, dtype=torch.int64).to(device, non_blocking=True)
+
+
+def _use_cuda_graph(args, gen_model, device):
+    flag = args.get('cuda_graph', os.environ.get('MMB_CUDA_GRAPH', '0'))
+    if str(flag) in ('0', 'False', 'false', ''):
+        return False
+    if torch.device(device).type != 'cuda':
+        return False
+    # BatchNorm1d in training mode keeps host-visible counters; the captured step supports
+    # LayerNorm / no norm (the sweep's other half falls back to the eager loop)
+    return not isinstance(getattr(gen_model, 'norm', None), nn.BatchNorm1d)
+
+
 def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epochs, lr, word_prob_fn,
                      device, validation_data=None, verbose=True):
     """reference simplesif.py:49-162.
@@ -101,6 +219,9 @@ def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epoc
     Minimises ``mean_b(-log p(text, audio, visual | latent_b))`` over the latent matrix (and
     the generator heads when ``train`` and not ``args['freeze_weights']``) with SGD/Adam.
     Returns ``(embeddings (N, d) float32 on device, (losses, all_valid_losses))``.
+
+    ``args['cuda_graph']`` (or MMB_CUDA_GRAPH=1) replays each step as one captured CUDA graph
+    (``GraphedStep``); the default is the eager loop, launch for launch what the reference does.
     """
     embeddings = torch.tensor(np.array(embed_arr, copy=True), device=device, dtype=torch.float32)
     embeddings.requires_grad = True
@@ -108,7 +229,13 @@ def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epoc
     grad_params = [embeddings]
     if train and not args['freeze_weights']:
         grad_params.extend(gen_model.parameters())
-    optimizer = _make_optimizer(args, grad_params, lr)
+    graphed = _use_cuda_graph(args, gen_model, device)
+    if graphed and args['optimizer'] == 'adam':
+        optimizer = optim.Adam(grad_params, lr=lr, capturable=True)
+    else:
+        optimizer = _make_optimizer(args, grad_params, lr)
+    stepper = GraphedStep(args, gen_model, embeddings, dataloader.dataset, optimizer, word_prob_fn,
+                          device) if graphed else None
 
     valid_niter = 10
     start_time = time.time()
@@ -117,19 +244,25 @@ def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epoc
     for i in range(n_epochs):
         epoch_loss = torch.zeros((), device=device)
         iters = 0
-        for x in dataloader:
-            j, batch_data, batch_masks = _batch_dicts(args, x)
-            iters += 1
-            optimizer.zero_grad()
-            out = gen_model(embeddings[j])
-            if verbose and i % valid_niter == 0 and iters == 1:
-                _warn_tiny_sigma(out)
-            log_prob = -get_log_prob_matrix(args, embeddings[j], out, batch_data, batch_masks, word_prob_fn,
-                                            device=device, verbose=False)
-            avg_log_prob = log_prob.mean()
-            avg_log_prob.backward()
-            optimizer.step()
-            epoch_loss += avg_log_prob.detach()
+        if graphed:
+            for j in _epoch_index_batches(dataloader, device):
+                iters += 1
+                epoch_loss += stepper(j)
+            stepper.check()
+        else:
+            for x in dataloader:
+                j, batch_data, batch_masks = _batch_dicts(args, x)
+                iters += 1
+                optimizer.zero_grad()
+                out = gen_model(embeddings[j])
+                if verbose and i % valid_niter == 0 and iters == 1:
+                    _warn_tiny_sigma(out)
+                log_prob = -get_log_prob_matrix(args, embeddings[j], out, batch_data, batch_masks, word_prob_fn,
+                                                device=device, verbose=False)
+                avg_log_prob = log_prob.mean()
+                avg_log_prob.backward()
+                optimizer.step()
+                epoch_loss += avg_log_prob.detach()
         losses.append(float(epoch_loss))
         if i % valid_niter == 0:
             if verbose:

@@ -188,3 +188,48 @@ def test_optimize_latents_matches_reference_loop(mods, golden_dir, tag):
     close(np.array(losses_), g[tag + '_losses'], 2e-4, 'losses')
     close(emb.cpu(), g[tag + '_emb'], 1e-3, 'latents')
     close(model.embed2out['audio']['mu'].weight.detach().cpu(), g[tag + '_Wmu_audio'], 1e-3, 'W')
+
+
+@pytest.mark.parametrize('tag', sorted(cases.OPT_CASES))
+@pytest.mark.parametrize('shuffle', [False, True])
+def test_cuda_graph_step_matches_eager_loop(mods, golden_dir, tag, shuffle):
+    """args['cuda_graph']: every step replayed as ONE captured CUDA graph gives
+    the eager loop's result -- same golden fixture (the reference's own loop) when the batch
+    order is fixed, and the same numbers as the eager loop under the same seed when shuffled
+    (the index batches come from the DataLoader's sampler with the same RNG draws)."""
+    torch, losses, models = mods
+    import simplesif
+    import utils
+    from torch.utils.data import DataLoader
+    g = np.load(os.path.join(golden_dir, 'optimize_latents.npz'))
+    cfg = cases.OPT_CASES[tag]
+    if cfg['inputs']['norm'] == 'batch_norm':
+        pytest.skip('BatchNorm1d keeps the eager loop')
+    c = cases.mmb_inputs(**cfg['inputs'])
+    dev = torch.device('cuda')
+
+    def run(graph):
+        model = models.AudioVisualGeneratorMultimodal(c['d'], c['A'], c['Vd'], norm=cfg['inputs']['norm'],
+                                                      frozen_weights=False, unimodal=cfg['inputs']['unimodal']).to(dev)
+        cases.load_heads(model, c['heads'], c.get('norm_params'))
+        ds = utils.MMData(c['text'], c['aud'], c['vis'], {'text': c['text_m'], 'covarep': c['aud_m'],
+                                                           'facet': c['vis_m']}, c['text_w'], dev)
+        torch.manual_seed(1234)
+        loader = DataLoader(ds, batch_size=cfg['batch'], shuffle=shuffle)
+        We_t = torch.tensor(c['We'], device=dev)
+        word_fn = simplesif.make_word_log_prob_fn({'word_sim_metric': 'angular'}, None, We_t)
+        args = dict(cfg['args'])
+        args['cuda_graph'] = 1 if graph else 0
+        emb, (ls, _) = simplesif.optimize_latents(args, cfg['train'], model, c['latents'], loader, cfg['epochs'],
+                                                  cfg['lr'], word_fn, dev, verbose=False)
+        return emb.cpu().numpy(), np.array(ls), model.embed2out['audio']['mu'].weight.detach().cpu().numpy()
+
+    emb_g, ls_g, W_g = run(True)
+    if not shuffle:
+        close(ls_g, g[tag + '_losses'], 2e-4, 'losses')
+        close(emb_g, g[tag + '_emb'], 1e-3, 'latents')
+        close(W_g, g[tag + '_Wmu_audio'], 1e-3, 'W')
+    emb_e, ls_e, W_e = run(False)
+    close(ls_g, ls_e, 1e-5, 'losses vs eager')
+    close(emb_g, emb_e, 1e-5, 'latents vs eager')
+    close(W_g, W_e, 1e-5, 'W vs eager')

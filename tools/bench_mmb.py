@@ -146,11 +146,21 @@ def run(name, steps, do_cpu):
 
     ours = make_loop(lambda m, e, b: ours_step(m, e, b, word_fn, losses), dev)
     ms_ours, l_ours = time_gpu(ours, steps)
+    # the same step replayed as one captured CUDA graph (simplesif.GraphedStep)
+    import utils
+    ds = utils.MMData(S['text'], S['aud'], S['vis'], {'text': S['text_m'], 'covarep': S['aud_m'], 'facet': S['vis_m']},
+                      S['text_w'], dev)
+    lat_g = S['latents'].clone().requires_grad_(True)
+    opt_g = torch.optim.SGD([lat_g] + list(model.parameters()), lr=1e-7)
+    stepper = simplesif.GraphedStep({'dataset': 'mosi', 'unimodal': False}, model, lat_g, ds, opt_g, word_fn, dev)
+    ms_graph, l_graph = time_gpu(lambda i: stepper(perm[(i % n_batches) * B:(i % n_batches + 1) * B]), steps)
+    stepper.check()
     stock = make_loop(lambda m, e, b: torch_step(m, e, b, S['table']), dev)
     ms_stock, l_stock = time_gpu(stock, max(5, steps // 5))
     res = {'metric': 'utterance-steps/s (one MMB2 fwd+bwd+SGD step, B=64)', 'shape': name,
            'N_T_V_A_Vd': SHAPES[name], 'steps': steps,
            'b200_fused': {'ms_per_step': ms_ours, 'value': B / ms_ours * 1e3, 'loss': l_ours},
+           'b200_fused_cuda_graph': {'ms_per_step': ms_graph, 'value': B / ms_graph * 1e3, 'loss': l_graph},
            'b200_stock_torch': {'ms_per_step': ms_stock, 'value': B / ms_stock * 1e3, 'loss': l_stock}}
     if do_cpu:
         cpu = make_loop(lambda m, e, b: torch_step(m, e, b, S['table'].cpu()), torch.device('cpu'))
