@@ -175,10 +175,13 @@ MMB_API int mmb_heads_forward(const float* z, int B, int d, int n_heads, const f
                       float* const* out, mmb_stream_t stream);
 /* Backward of the above given gout[h] (B, D[h]) = d loss / d pre-activation of head h:
  * dz (B, d) = sum_h gout[h] W[h];  dW[h] (D[h], d) = gout[h]^T z;  db[h] (D[h]) = column sums.
- * dz, dW, db may be NULL (frozen heads, reference models.py:173-178).                   */
+ * dz, dW, db may be NULL (frozen heads, reference models.py:173-178).  dz is a split-K product
+ * (sum of D[h] in the thousands spread over ~100 CTAs, partials added in a fixed order): `ws`
+ * must hold mmb_heads_backward_workspace_bytes(B, d, n_heads, D) bytes when dz != NULL.   */
+MMB_API size_t mmb_heads_backward_workspace_bytes(int B, int d, int n_heads, const int* D);
 MMB_API int mmb_heads_backward(const float* z, int B, int d, int n_heads, const float* const* W,
                        const int* D, const float* const* gout, float* dz, float* const* dW,
-                       float* const* db, mmb_stream_t stream);
+                       float* const* db, void* ws, size_t ws_bytes, mmb_stream_t stream);
 
 /* get_normal_log_prob -- losses.py:13-34 for n_mod modalities in ONE launch: value and the
  * analytic gradients.  Modality m is the concatenation along the

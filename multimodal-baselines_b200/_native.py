@@ -55,7 +55,8 @@ SIGNATURES = {
     'mmb_allreduce_peer': (_i, [_p, _i64, _i, _i, _i, _p, C.c_uint64, _p, _p]),
     'mmb_gram_allreduce_peer': (_i, [_p, _i64, _i, _p, _p, _sz, _i, _i, _i, _p, C.c_uint64, _p, _p]),
     'mmb_heads_forward': (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
-    'mmb_heads_backward': (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    'mmb_heads_backward_workspace_bytes': (_sz, [_i, _i, _i, _p]),
+    'mmb_heads_backward': (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     'mmb_gauss_ll': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'mmb_row_inv_norm': (_i, [_p, _i64, _i, _p, _p]),
     'mmb_word_ll_workspace_bytes': (_sz, [_i, _i64, _i]),

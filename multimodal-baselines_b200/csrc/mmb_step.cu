@@ -74,6 +74,26 @@ __device__ __forceinline__ void zero_acc(float (&acc)[4][4]) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 }
 
+// out[i] = sum_s part[s][i] in split order (deterministic): second stage of the split-K products
+// below, which spread a (64 x K) x (K x d) product with K in the thousands over ~100 CTAs instead
+// of d / 64 = 5.
+__global__ void __launch_bounds__(256)
+    splitk_reduce_kernel(const float* __restrict__ part, int n_split, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < n_split; ++k) s += part[(size_t)k * n + i];
+  out[i] = s;
+}
+
+constexpr int kMaxDzItems = 96;
+struct DzItems {          // split-K work items of heads_bwd_dz: rows [k0, k0 + klen) of head h
+  unsigned char h[kMaxDzItems];
+  short k0[kMaxDzItems];
+  short klen[kMaxDzItems];
+  int n_items;
+};
+
 // ---------------------------------------------------------------- heads (A6) ---------
 struct HeadsArgs {
   const float* W[kMaxHeads];
@@ -113,15 +133,18 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// dz[m][n] = sum_h sum_k gout[h][m][k] W[h][k][n]; grid (n tiles over d, m tiles)
+// dz[m][n] = sum_h sum_k gout[h][m][k] W[h][k][n]; grid (n tiles over d, m tiles, split-K items):
+// item z handles rows [k0, k0 + klen) of head h and writes its partial tile to part[z][m][n].
 __global__ void __launch_bounds__(256)
-    heads_bwd_dz_kernel(float* __restrict__ dz, int B, int d, const __grid_constant__ HeadsArgs args) {
+    heads_bwd_dz_kernel(float* __restrict__ part, int B, int d, const __grid_constant__ HeadsArgs args,
+                        const __grid_constant__ DzItems items) {
   __shared__ TileSmem sm;
   const int n0 = blockIdx.x * kTN, m0 = blockIdx.y * kTM;
+  const int it = blockIdx.z, h = items.h[it], k0 = items.k0[it], klen = items.klen[it];
   float acc[4][4];
   zero_acc(acc);
-  for (int h = 0; h < args.n_heads; ++h)
-    tile_gemm_accum(sm, acc, args.gout[h], args.D[h], 1, args.W[h], d, 1, m0, n0, B, d, args.D[h]);
+  tile_gemm_accum(sm, acc, args.gout[h] + k0, args.D[h], 1, args.W[h] + (size_t)k0 * d, d, 1, m0, n0, B, d, klen);
+  float* out = part + (size_t)it * B * d;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -130,7 +153,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
-      if (n < d) dz[(size_t)m * d + n] = acc[i][j];
+      if (n < d) out[(size_t)m * d + n] = acc[i][j];
     }
   }
 }
@@ -271,15 +294,19 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Hsum[b][:] = sum_v Hw[b][v] * W[v][:]   ((B x V) x (V x d))
+// Hsum[b][:] = sum_v Hw[b][v] * W[v][:]   ((B x V) x (V x d)), split over V: CTA z handles
+// rows [z * vchunk, (z + 1) * vchunk) of the table and writes part[z][b][:].
 __global__ void __launch_bounds__(256)
-    word_h_kernel(const float* __restrict__ Hw, const float* __restrict__ W, int B, int V, int d,
-                  float* __restrict__ Hsum) {
+    word_h_kernel(const float* __restrict__ Hw, const float* __restrict__ W, int B, int V, int d, int vchunk,
+                  float* __restrict__ part) {
   __shared__ TileSmem sm;
   const int n0 = blockIdx.x * kTN, m0 = blockIdx.y * kTM;
+  const int v0 = blockIdx.z * vchunk;
+  const int vlen = (V - v0) < vchunk ? (V - v0) : vchunk;
   float acc[4][4];
   zero_acc(acc);
-  tile_gemm_accum(sm, acc, Hw, V, 1, W, d, 1, m0, n0, B, d, V);
+  tile_gemm_accum(sm, acc, Hw + v0, V, 1, W + (size_t)v0 * d, d, 1, m0, n0, B, d, vlen);
+  float* out = part + (size_t)blockIdx.z * B * d;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -288,7 +315,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
-      if (n < d) Hsum[(size_t)m * d + n] = acc[i][j];
+      if (n < d) out[(size_t)m * d + n] = acc[i][j];
     }
   }
 }
@@ -403,16 +430,40 @@ extern "C" int mmb_heads_forward(const float* z, int B, int d, int n_heads, cons
   return MMB_OK;
 }
 
+static const int kDzChunk = 128;   // rows of W per split-K item
+
+static int dz_items(int n_heads, const int* D, DzItems* it) {
+  int n = 0;
+  for (int h = 0; h < n_heads; ++h)
+    for (int k0 = 0; k0 < D[h]; k0 += kDzChunk) {
+      if (n >= kMaxDzItems) return -1;
+      if (it) {
+        it->h[n] = (unsigned char)h;
+        it->k0[n] = (short)k0;
+        it->klen[n] = (short)((D[h] - k0) < kDzChunk ? (D[h] - k0) : kDzChunk);
+      }
+      ++n;
+    }
+  if (it) it->n_items = n;
+  return n;
+}
+
+extern "C" size_t mmb_heads_backward_workspace_bytes(int B, int d, int n_heads, const int* D) {
+  if (!D || n_heads <= 0) return 0;
+  const int n = dz_items(n_heads, D, nullptr);
+  return n > 0 ? (size_t)n * B * d * sizeof(float) : 0;
+}
+
 extern "C" int mmb_heads_backward(const float* z, int B, int d, int n_heads, const float* const* W,
                                   const int* D, const float* const* gout, float* dz, float* const* dW,
-                                  float* const* db, mmb_stream_t stream) {
+                                  float* const* db, void* ws, size_t ws_bytes, mmb_stream_t stream) {
   MMB_REQUIRE(z && W && D && gout, "null pointer");
   MMB_REQUIRE(n_heads > 0 && n_heads <= kMaxHeads, "1..16 heads");
   MMB_REQUIRE(B > 0 && d > 0, "bad size");
   HeadsArgs a = {};
   int max_D = 0;
   for (int h = 0; h < n_heads; ++h) {
-    MMB_REQUIRE(W[h] && gout[h] && D[h] > 0, "null head");
+    MMB_REQUIRE(W[h] && gout[h] && D[h] > 0 && D[h] < 32768, "null head / head too wide");
     a.W[h] = W[h]; a.gout[h] = gout[h]; a.D[h] = D[h];
     a.dW[h] = dW ? dW[h] : nullptr;
     a.db[h] = db ? db[h] : nullptr;
@@ -421,9 +472,14 @@ extern "C" int mmb_heads_backward(const float* z, int B, int d, int n_heads, con
   a.n_heads = n_heads;
   cudaStream_t st = as_stream(stream);
   if (dz) {
-    dim3 grid((d + kTN - 1) / kTN, (B + kTM - 1) / kTM);
-    heads_bwd_dz_kernel<<<grid, 256, 0, st>>>(dz, B, d, a);
+    DzItems items = {};
+    MMB_REQUIRE(dz_items(n_heads, D, &items) > 0, "too many split-K items (sum of ceil(D / 128) must be <= 96)");
+    MMB_REQUIRE(ws && ws_bytes >= mmb_heads_backward_workspace_bytes(B, d, n_heads, D), "workspace too small");
+    dim3 grid((d + kTN - 1) / kTN, (B + kTM - 1) / kTM, items.n_items);
+    heads_bwd_dz_kernel<<<grid, 256, 0, st>>>((float*)ws, B, d, a, items);
     MMB_LAUNCH_CHECK("heads_bwd_dz");
+    splitk_reduce_kernel<<<(B * d + 255) / 256, 256, 0, st>>>((const float*)ws, items.n_items, B * d, dz);
+    MMB_LAUNCH_CHECK("heads_bwd_dz_reduce");
   }
   if (dW) {
     for (int h = 0; h < n_heads; ++h) MMB_REQUIRE(dW[h], "null dW");
@@ -472,9 +528,14 @@ extern "C" int mmb_row_inv_norm(const float* X, int64_t n, int d, float* inv_nor
   return MMB_OK;
 }
 
+static int word_h_splits(int64_t V) {   // ~192 table rows per split-K slice, at most 64 slices
+  int64_t n = (V + 191) / 192;
+  return (int)(n < 1 ? 1 : (n > 64 ? 64 : n));
+}
+
 extern "C" size_t mmb_word_ll_workspace_bytes(int B, int64_t V, int d) {
-  // S, Hw, Q: (B, V) each; Hsum: (B, d); ie: (B)
-  return ((size_t)3 * B * V + (size_t)B * d + B) * sizeof(float) + 256;
+  // S, Hw, Q: (B, V) each; Hsum: (B, d); ie: (B); split-K partials of Hsum: (splits, B, d)
+  return ((size_t)3 * B * V + (size_t)B * d + B + (size_t)word_h_splits(V) * B * d) * sizeof(float) + 256;
 }
 
 extern "C" int mmb_word_ll(const float* latents, int B, int d, const float* table, const float* inv_norm,
@@ -493,14 +554,19 @@ extern "C" int mmb_word_ll(const float* latents, int B, int d, const float* tabl
   float* Q = Hw + (size_t)B * V;
   float* Hsum = Q + (size_t)B * V;
   float* ie = Hsum + (size_t)B * d;
+  float* hpart = ie + B;
   row_inv_norm_kernel<<<(B + 7) / 8, 256, 0, st>>>(latents, B, d, ie);
   MMB_LAUNCH_CHECK("row_inv_norm(latents)");
   dim3 g1((unsigned)((V + kTN - 1) / kTN), (B + kTM - 1) / kTM);
   word_cos_kernel<<<g1, 256, 0, st>>>(latents, ie, B, d, table, inv_norm, (int)V, S, Hw, Q);
   MMB_LAUNCH_CHECK("word_cos");
-  dim3 g2((d + kTN - 1) / kTN, (B + kTM - 1) / kTM);
-  word_h_kernel<<<g2, 256, 0, st>>>(Hw, table, B, (int)V, d, Hsum);
+  const int splits = word_h_splits(V);
+  const int vchunk = (int)(((V + splits - 1) / splits + kTK - 1) / kTK * kTK);
+  dim3 g2((d + kTN - 1) / kTN, (B + kTM - 1) / kTM, (unsigned)((V + vchunk - 1) / vchunk));
+  word_h_kernel<<<g2, 256, 0, st>>>(Hw, table, B, (int)V, d, vchunk, hpart);
   MMB_LAUNCH_CHECK("word_h");
+  splitk_reduce_kernel<<<(B * d + 255) / 256, 256, 0, st>>>(hpart, (int)g2.z, B * d, Hsum);
+  MMB_LAUNCH_CHECK("word_h_reduce");
   word_finish_kernel<<<B, 256, 2 * L * sizeof(float), st>>>(latents, ie, B, d, (int)V, S, Q, Hsum, sent,
                                                           sent_stride_b, sent_stride_t, word_w, tmask,
                                                           tmask_stride_b, tmask_stride_t, L, a, lp, grad, status);

@@ -68,9 +68,13 @@ class HeadsFunction(torch.autograd.Function):
         dz = torch.empty_like(z) if need_z else None
         dWs = [torch.empty_like(w) for w in Ws] if need_w else None
         dbs = [torch.empty(D, dtype=torch.float32, device=z.device) for D in ctx.Ds] if need_w else None
-        nv.check(lib.mmb_heads_backward(nv.ptr(z), B, d, n, _ptr_array(Ws), _int_array(ctx.Ds), _ptr_array(gpre),
+        Ds_c = _int_array(ctx.Ds)
+        nbytes = lib.mmb_heads_backward_workspace_bytes(B, d, n, Ds_c) if need_z else 0
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=z.device)
+        nv.check(lib.mmb_heads_backward(nv.ptr(z), B, d, n, _ptr_array(Ws), Ds_c, _ptr_array(gpre),
                                         nv.ptr(dz), _ptr_array(dWs) if need_w else None,
-                                        _ptr_array(dbs) if need_w else None, nv.stream_ptr()))
+                                        _ptr_array(dbs) if need_w else None, nv.ptr(ws), nbytes,
+                                        nv.stream_ptr()))
         grads = [dz, None]
         for h in range(n):
             grads.append(dWs[h] if need_w and ctx.needs_input_grad[2 + 2 * h] else None)
