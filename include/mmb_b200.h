@@ -214,6 +214,22 @@ MMB_API int mmb_word_ll(const float* latents, int B, int d, const float* table, 
                 int64_t tmask_stride_t, int L, float a, float* lp, float* grad, void* ws,
                 size_t ws_bytes, int* status, mmb_stream_t stream);
 
+/* ---------------------------------------------------------------- closed form (N1) */
+/* estimate_embedding_overall_gpu2 -- sif2.py:164-208 with calc_weights sif2.py:103-114 (call site
+ * simplesif.py:808-880): gradient-free latents as the weight-normalised, L2-normalised sum of the
+ * SIF text average and per-modality q_mean W_mu + q_sigma W_log_sigma terms.
+ * Step 1, one pass over the base tensors (modalities = concatenations of segments, as in
+ * mmb_gauss_ll): S1[m], S2[m] (N, D_m) = sums over time of q_mean, q_sigma, and
+ * tw_part (n_mod, N) = their sums over features.  Step 2: prod (N, d) = sum_m S1[m] W_mu[m] +
+ * S2[m] W_ls[m] with mmb_heads_backward (dz only; gout = S1/S2, W = the (D_m, d) weights).
+ * Step 3: out (N, d) = normalise((sum_t sent_w[n,t] emb[n,t,:] + prod) / tw).              */
+MMB_API int mmb_closed_form_stats(int N, int T, int n_mod, const int* n_seg, const float* const* seg_val,
+                          const int* seg_F, const float* const* b_mu, const float* const* b_ls,
+                          float* const* S1, float* const* S2, float* tw_part, mmb_stream_t stream);
+MMB_API int mmb_closed_form_finish(int N, int L, int d, const float* sent_w, const float* emb,
+                           const float* prod, const float* tw_part, int n_mod, float* out,
+                           mmb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

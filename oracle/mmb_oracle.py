@@ -201,3 +201,32 @@ def concat_modalities(text_gauss, aud, vis, unimodal=False):
         d['textvisual'] = np.concatenate([text_gauss, vis], -1)
         d['textaudiovisual'] = np.concatenate([text_gauss, aud, vis], -1)
     return d
+
+
+# --------------------------------------------------------------------------- closed form (N1)
+def calc_weights(data, b_mean, b_log_sigma, mask=None):
+    """reference sif2.py:103-114: q_mean = (x - b_mu) / exp(2 b_ls), q_sigma = (x - b_mu)^2 /
+    exp(2 b_ls) - 1 (the mask argument is unused there too)."""
+    data = np.asarray(data, dtype=np.float64)
+    bm = np.asarray(b_mean, dtype=np.float64).reshape(1, 1, -1)
+    bl = np.asarray(b_log_sigma, dtype=np.float64).reshape(1, 1, -1)
+    return (data - bm) / np.exp(2 * bl), (data - bm) ** 2 / np.exp(2 * bl) - 1.0
+
+
+def estimate_embedding_overall(data, heads, sentence_weights, embeddings, keys):
+    """reference sif2.py:164-208 (estimate_embedding_overall_gpu2) in float64.
+    data[k] (N, T, D_k); heads[k] = (W_mu, b_mu, W_ls, b_ls); sentence_weights (N, L);
+    embeddings (N, L, d).  Returns (N, d) unit rows."""
+    sw = np.asarray(sentence_weights, dtype=np.float64)
+    E = np.asarray(embeddings, dtype=np.float64)
+    qm, qs = {}, {}
+    for k in keys:
+        Wm, bm, Ws, bs = heads[k]
+        qm[k], qs[k] = calc_weights(data[k], bm, bs)
+    tw = sw.sum(-1) + sum(q.sum(-1).sum(-1) for q in qm.values()) + sum(q.sum(-1).sum(-1) for q in qs.values())
+    cs = np.einsum('nl,nld->nd', sw, E)
+    for k in keys:
+        Wm, bm, Ws, bs = heads[k]
+        cs = cs + qm[k].sum(1) @ np.asarray(Wm, dtype=np.float64) + qs[k].sum(1) @ np.asarray(Ws, dtype=np.float64)
+    cs = cs / tw[:, None]
+    return cs / np.linalg.norm(cs, axis=1, keepdims=True)

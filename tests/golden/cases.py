@@ -174,3 +174,19 @@ def raw_split(n=7, T=6, A=9, Vd=5, seed=51):
     cov[np.broadcast_to(pad, cov.shape)] = 0.0
     fac[np.broadcast_to(pad, fac.shape)] = 0.0
     return {'covarep': cov, 'facet': fac}
+
+
+CLOSED_FORM_CASES = {
+    # estimate_embedding_overall_gpu2 (reference sif2.py:164-208) on one split of mmb_inputs
+    'mmb2_small': dict(B=9, T=6, d=24, A=6, Vd=5, V=40, seed=61, norm=None, unimodal=False, args={}),
+    'mmb2_mosi': dict(B=70, T=20, d=300, A=76, Vd=49, V=300, seed=62, norm=None, unimodal=False, args={}),
+}
+CLOSED_FORM_KEYS = ['audio', 'visual', 'audiovisual', 'textaudio', 'textvisual', 'textaudiovisual']
+
+
+def closed_form_data(c):
+    """The concatenated modalities the reference's call site builds (simplesif.py:826-846)."""
+    cat = lambda *xs: np.concatenate(xs, axis=-1)
+    return {'audio': c['aud'], 'visual': c['vis'], 'audiovisual': cat(c['aud'], c['vis']),
+            'textaudio': cat(c['text'], c['aud']), 'textvisual': cat(c['text'], c['vis']),
+            'textaudiovisual': cat(c['text'], c['aud'], c['vis'])}

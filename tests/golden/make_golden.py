@@ -181,6 +181,28 @@ def golden_optimize_latents():
     save('optimize_latents.npz', **out)
 
 
+def golden_closed_form():
+    """reference sif2.estimate_embedding_overall_gpu2 (the closed-form latents timed under
+    --time_test, simplesif.py:808-880) on seeded splits; sif2 imports utils -> h5py is stubbed."""
+    import utils_stub  # noqa: F401  (installs the h5py stub)
+    import sif2 as ref_sif2
+    assert ref_sif2.__file__.startswith(REF)
+    out = {}
+    for tag, cfg in cases.CLOSED_FORM_CASES.items():
+        c = cases.mmb_inputs(**cfg)
+        model = ref_models.AudioVisualGeneratorMultimodal(c['d'], c['A'], c['Vd'], norm=None, frozen_weights=True,
+                                                          unimodal=False)
+        cases.load_heads(model, c['heads'])
+        data = {k: torch.tensor(v) for k, v in cases.closed_form_data(c).items()}
+        networks = {k: (model.embed2out[k]['mu'], model.embed2out[k]['log_sigma']) for k in cases.CLOSED_FORM_KEYS}
+        with torch.no_grad():
+            cs = ref_sif2.estimate_embedding_overall_gpu2(data, {k: None for k in data}, networks, torch.tensor(c['text_w']),
+                                                         torch.tensor(c['text']))
+        out[tag + '_cs'] = cs.numpy()
+        out[tag + '_check'] = cases.checksum(c['text']) + cases.checksum(c['aud'])
+    save('closed_form.npz', **out)
+
+
 def golden_utils():
     """Reference utils.py preprocessing (normalize_data 155-191, add_positional_embeddings
     130-153, quirks included) on a small seeded split."""
@@ -192,7 +214,12 @@ def golden_utils():
          m_facet=masks['facet'])
 
 
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'closed_form':
+    golden_closed_form()
+    sys.exit(0)
+
 if __name__ == '__main__':
     main()
     golden_optimize_latents()
     golden_utils()
+    golden_closed_form()

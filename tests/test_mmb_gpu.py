@@ -233,3 +233,38 @@ def test_cuda_graph_step_matches_eager_loop(mods, golden_dir, tag, shuffle):
     close(ls_g, ls_e, 1e-5, 'losses vs eager')
     close(emb_g, emb_e, 1e-5, 'latents vs eager')
     close(W_g, W_e, 1e-5, 'W vs eager')
+
+
+@pytest.mark.parametrize('tag', sorted(cases.CLOSED_FORM_CASES))
+@pytest.mark.parametrize('segments', [False, True])
+def test_closed_form_estimate(mods, golden_dir, tag, segments):
+    """sif2.estimate_embedding_overall_gpu2 against the reference's output and
+    the float64 oracle; `segments` feeds the base tensors (CatSegments) instead of torch.cat."""
+    torch, losses, models = mods
+    import sif2
+    from oracle import mmb_oracle as mo
+    g = np.load(os.path.join(golden_dir, 'closed_form.npz'))
+    c = cases.mmb_inputs(**cases.CLOSED_FORM_CASES[tag])
+    dev = torch.device('cuda')
+    model = models.AudioVisualGeneratorMultimodal(c['d'], c['A'], c['Vd'], norm=None, frozen_weights=True,
+                                                  unimodal=False).to(dev)
+    cases.load_heads(model, c['heads'])
+    t = lambda a: torch.tensor(a, device=dev)
+    if segments:
+        text, aud, vis = t(c['text']), t(c['aud']), t(c['vis'])
+        C = losses.CatSegments
+        data = {'audio': aud, 'visual': vis, 'audiovisual': C([aud, vis]), 'textaudio': C([text, aud]),
+                'textvisual': C([text, vis]), 'textaudiovisual': C([text, aud, vis])}
+    else:
+        data = {k: t(v) for k, v in cases.closed_form_data(c).items()}
+    networks = {k: (model.embed2out[k]['mu'], model.embed2out[k]['log_sigma']) for k in cases.CLOSED_FORM_KEYS}
+    cs = sif2.estimate_embedding_overall_gpu2(data, None, networks, t(c['text_w']), t(c['text']))
+    assert cs.shape == (c['text'].shape[0], c['d'])
+    want = mo.estimate_embedding_overall(cases.closed_form_data(c), c['heads'], c['text_w'], c['text'],
+                                         cases.CLOSED_FORM_KEYS)
+    close(cs.cpu(), want, 2e-5, 'closed form vs oracle')
+    close(cs.cpu(), g[tag + '_cs'], 2e-5, 'closed form vs reference')
+    qm, qs = sif2.calc_weights(t(c['aud']), model.embed2out['audio']['mu'].bias, model.embed2out['audio']['log_sigma'].bias, None)
+    wm, wsg = mo.calc_weights(c['aud'], c['heads']['audio'][1], c['heads']['audio'][3])
+    close(qm.detach().cpu(), wm, 1e-5, 'q_mean')
+    close(qs.detach().cpu(), wsg, 1e-5, 'q_sigma')
