@@ -56,6 +56,49 @@ def predict_sentiment(data, model, latents):
     return p.cpu().numpy(), y.cpu().numpy()
 
 
+class _GraphedSentimentStep(object):
+    """One SGD step of the regressor (forward, L1, backward, update) captured as a CUDA graph per
+    batch size and replayed; numerically the eager step on the same indices."""
+
+    def __init__(self, model, latents, labels, optimizer):
+        self.model, self.latents, self.labels, self.optimizer = model, latents, labels, optimizer
+        self.graphs = {}
+
+    def _step(self, j):
+        senti = self.labels[j]
+        loss = (self.model(self.latents[j]).reshape(senti.shape) - senti).abs().mean()
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    def __call__(self, j):
+        n = int(j.shape[0])
+        if n not in self.graphs:
+            dev = self.latents.device
+            static_j = torch.zeros(n, dtype=torch.int64, device=dev)
+            params = [p for g in self.optimizer.param_groups for p in g['params']]
+            saved = [p.detach().clone() for p in params]
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self.optimizer.zero_grad(set_to_none=True)
+                    self._step(static_j)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            with torch.no_grad():
+                for p, s in zip(params, saved):
+                    p.copy_(s)
+            graph = torch.cuda.CUDAGraph()
+            self.optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                static_loss = self._step(static_j)
+            self.graphs[n] = (graph, static_j, static_loss)
+        graph, static_j, static_loss = self.graphs[n]
+        static_j.copy_(j)
+        graph.replay()
+        return static_loss
+
+
 def train_sentiment(args, model, train_data, train_latents, valid_data=None, valid_latents=None,
                     model_save_path=None):
     """reference sentiment_model.py:76-163 -- SGD on the L1 loss; with ``early_stopping`` the best
@@ -64,14 +107,24 @@ def train_sentiment(args, model, train_data, train_latents, valid_data=None, val
     optimizer = optim.SGD(model.parameters(), lr=lr)
     best, best_state, patience, trials = float('inf'), None, 0, 0
     train_losses, valid_losses = [], []
+    graphed = str(args.get('cuda_graph', 0)) not in ('0', 'False', 'false', '') and train_latents.is_cuda
+    stepper = _GraphedSentimentStep(model, train_latents, train_data.dataset.sentiment, optimizer) if graphed else None
     for _ in range(args['n_sentiment_epochs']):
-        total = 0.
-        for j, senti in train_data:
-            optimizer.zero_grad()
-            loss = (model(train_latents[j]).reshape(senti.shape) - senti).abs().mean()
-            loss.backward()
-            optimizer.step()
-            total += float(loss)
+        if graphed:
+            # each SGD step is one graph replay; the epoch loss is read back once
+            total_t = torch.zeros((), device=train_latents.device)
+            torch.empty((), dtype=torch.int64).random_(generator=train_data.generator)   # the DataLoader's base seed
+            for idx in train_data.batch_sampler:
+                total_t += stepper(torch.as_tensor(idx, dtype=torch.int64).to(train_latents.device, non_blocking=True))
+            total = float(total_t)
+        else:
+            total = 0.
+            for j, senti in train_data:
+                optimizer.zero_grad()
+                loss = (model(train_latents[j]).reshape(senti.shape) - senti).abs().mean()
+                loss.backward()
+                optimizer.step()
+                total += float(loss)
         train_losses.append(total)
         if args.get('early_stopping') and valid_data is not None:
             with torch.no_grad():
@@ -90,6 +143,8 @@ def train_sentiment(args, model, train_data, train_latents, valid_data=None, val
                     lr = lr * args.get('lr_decay', 0.5)
                     model.load_state_dict(best_state)
                     optimizer = optim.SGD(model.parameters(), lr=lr)
+                    if graphed:
+                        stepper = _GraphedSentimentStep(model, train_latents, train_data.dataset.sentiment, optimizer)
     if best_state is not None:
         model.load_state_dict(best_state)
     return train_losses, valid_losses

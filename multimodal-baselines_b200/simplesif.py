@@ -105,8 +105,12 @@ class GraphedStep(object):
     The captured work is exactly what the eager loop of ``optimize_latents`` runs on the same
     indices, so the results agree to rounding (tests/test_mmb_gpu.py)."""
 
-    def __init__(self, args, gen_model, embeddings, dataset, optimizer, word_prob_fn, device):
+    def __init__(self, args, gen_model, embeddings, dataset, optimizer, word_prob_fn, device, extra_loss=None,
+                 extra_modules=()):
+        """``extra_loss(j, latents_j, neg_log_prob)`` -> per-utterance loss (the e2e loop mixes in the
+        sentiment regressor's L1 term); ``extra_modules`` are restored with the rest after warm-up."""
         import mmb_ops
+        self.extra_loss, self.extra_modules = extra_loss, list(extra_modules)
         self.args, self.gen_model, self.embeddings = args, gen_model, embeddings
         self.dataset, self.optimizer, self.word_prob_fn, self.device = dataset, optimizer, word_prob_fn, device
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
@@ -120,6 +124,8 @@ class GraphedStep(object):
         out = self.gen_model(e)
         log_prob = -get_log_prob_matrix(self.args, e, out, batch_data, batch_masks, self.word_prob_fn,
                                         device=self.device, verbose=False)
+        if self.extra_loss is not None:
+            log_prob = self.extra_loss(j, e, log_prob)
         loss = log_prob.mean()
         loss.backward()
         self.optimizer.step()
@@ -128,14 +134,20 @@ class GraphedStep(object):
     def _snapshot(self):
         params = [p for g in self.optimizer.param_groups for p in g['params']]
         saved = [p.detach().clone() for p in params]
-        bufs = [b.detach().clone() for b in self.gen_model.buffers()]
+        bufs = [b.detach().clone() for b in self._buffers()]
         return params, saved, bufs
+
+    def _buffers(self):
+        out = list(self.gen_model.buffers())
+        for m in self.extra_modules:
+            out.extend(m.buffers())
+        return out
 
     def _restore(self, params, saved, bufs):
         with torch.no_grad():
             for p, s in zip(params, saved):
                 p.copy_(s)
-            for b, s in zip(self.gen_model.buffers(), bufs):
+            for b, s in zip(self._buffers(), bufs):
                 b.copy_(s)
             for st in self.optimizer.state.values():     # Adam moments / step counters back to zero
                 for v in st.values():
@@ -308,30 +320,47 @@ def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, 
     train_embed = torch.tensor(np.array(train_embedding, copy=True), device=device, dtype=torch.float32)
     train_embed.requires_grad = True
     grad_params = [train_embed] + list(gen_model.parameters()) + list(senti_model.parameters())
-    optimizer = _make_optimizer(args, grad_params, args['lr'])
+    graphed = _use_cuda_graph(args, gen_model, device)
+    if graphed and args['optimizer'] == 'adam':
+        optimizer = optim.Adam(grad_params, lr=args['lr'], capturable=True)
+    else:
+        optimizer = _make_optimizer(args, grad_params, args['lr'])
     loss_function = nn.L1Loss(reduction='none')
     like_w = args['likelihood_weight']
+
+    def mixed_loss(j, e, log_prob):
+        """reference simplesif.py:776-786: L1 sentiment term, masked, mixed with the likelihood."""
+        _, s_data = senti_train_data[j]
+        senti_loss = loss_function(senti_model(e), s_data)
+        if senti_loss.dim() > 1:
+            senti_loss = senti_loss.mean(-1)
+        senti_loss = senti_loss * senti_mask[j].reshape(senti_loss.shape)
+        return like_w * log_prob + (1. - like_w) * senti_loss
+
+    stepper = GraphedStep(args, gen_model, train_embed, dataloader.dataset, optimizer, word_prob_fn, device,
+                          extra_loss=mixed_loss, extra_modules=[senti_model]) if graphed else None
     train_losses = []
     start_time = time.time()
     for i in range(n_epochs if n_epochs is not None else args['n_epochs']):
         epoch_loss = torch.zeros((), device=device)
         iters = 0
-        for x in dataloader:
-            j, batch_data, batch_masks = _batch_dicts(args, x)
-            _, s_data = senti_train_data[j]
-            iters += 1
-            optimizer.zero_grad()
-            out = gen_model(train_embed[j])
-            log_prob = -get_log_prob_matrix(args, train_embed[j], out, batch_data, batch_masks, word_prob_fn,
-                                            device=device, verbose=False)
-            senti_loss = loss_function(senti_model(train_embed[j]), s_data)
-            if senti_loss.dim() > 1:
-                senti_loss = senti_loss.mean(-1)
-            senti_loss = senti_loss * senti_mask[j].reshape(senti_loss.shape)
-            loss = (like_w * log_prob + (1. - like_w) * senti_loss).mean()
-            loss.backward()
-            optimizer.step()
-            epoch_loss += loss.detach()
+        if graphed:
+            for j in _epoch_index_batches(dataloader, device):
+                iters += 1
+                epoch_loss += stepper(j)
+            stepper.check()
+        else:
+            for x in dataloader:
+                j, batch_data, batch_masks = _batch_dicts(args, x)
+                iters += 1
+                optimizer.zero_grad()
+                out = gen_model(train_embed[j])
+                log_prob = -get_log_prob_matrix(args, train_embed[j], out, batch_data, batch_masks, word_prob_fn,
+                                                device=device, verbose=False)
+                loss = mixed_loss(j, train_embed[j], log_prob).mean()
+                loss.backward()
+                optimizer.step()
+                epoch_loss += loss.detach()
         train_losses.append(float(epoch_loss))
         if verbose and i % 10 == 0:
             print("epoch {}: {} ({}s)".format(i, train_losses[-1] / max(iters, 1), time.time() - start_time))

@@ -98,3 +98,19 @@ def test_metrics_keys():
     assert set(r) == {'mae', 'accuracy', 'corr', 'mult_acc', 'f_score', 'confusion_matrix', 'class_report'}
     r = losses.pom_loss(rng.uniform(1, 7, (20, 3)), rng.uniform(1, 7, (20, 3)))
     assert set(r) == {'mae', 'corr', 'mult_acc', 'f_score'} and len(r['mae']) == 3
+
+
+def test_sweep_grid_matches_reference_generator():
+    """sweep.make_grid is the 2^9 grid of reference configs/make_configs.py:16-32 in product order."""
+    import sweep
+    grid = sweep.make_grid()
+    assert len(grid) == 512 and [c['config_num'] for c in grid] == list(range(512))
+    varied = [k for k, v in sweep.GRID.items() if len(v) == 2]
+    assert sorted(varied) == sorted(['sentiment_hidden_size', 'lr', 'sentiment_lr', 'n_epochs', 'word_loss_weight',
+                                     'likelihood_weight', 'pos_embed_dim', 'norm', 'optimizer'])
+    assert len({tuple(c[k] for k in varied) for c in grid}) == 512
+    assert all(c['e2e'] is True and c['n_sentiment_epochs'] == 400 and c['seq_len'] == 20 for c in grid)
+    We, weights, splits = sweep.synthetic_mosi(sizes=(30, 10, 12))
+    assert We.shape == (3016, 300) and weights.shape == (3016,) and weights[0] == 1.0
+    assert [s['text'].shape for s in splits] == [(30, 20), (10, 20), (12, 20)]
+    assert all((s['covarep'][s['text'] == 0] == 0).all() for s in splits)
