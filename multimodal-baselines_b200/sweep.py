@@ -148,10 +148,14 @@ def run_config(cfg, prep, epochs_scale=1.0, cuda_graph=True, verbose=False):
                                                unimodal=False).to(device)
     senti_model = SentimentModel(d, args['sentiment_hidden_size'], 1).to(device)
     senti_mask = torch.ones(len(prep.labels[0]), device=device)
-    quiet = open(os.devnull, 'w') if not verbose else None
+    # The reference's helpers print progress and, on a non-finite log-probability, print the
+    # modality names and sys.exit() (losses.py:258-264) -- in the reference one config is one
+    # process; here that exit marks the config as diverged and the sweep goes on.
+    import io
+    buf = io.StringIO()
     old_stdout = sys.stdout
-    if quiet:
-        sys.stdout = quiet
+    if not verbose:
+        sys.stdout = buf
     try:
         train_embed, train_losses = simplesif.train_end_to_end(
             args, gen_model, senti_model, prep.embeddings[0], loaders[0], SentimentData(prep.labels[0], device),
@@ -163,10 +167,12 @@ def run_config(cfg, prep, epochs_scale=1.0, cuda_graph=True, verbose=False):
                                                                   device, verbose=False)
         results, _ = train_sentiment_for_latents(args, (train_embed, valid_embed, test_embed), tuple(prep.labels),
                                                  device)
+    except SystemExit:
+        sys.stdout = old_stdout
+        tail = ' | '.join(buf.getvalue().strip().splitlines()[-7:])
+        return {'config_num': cfg['config_num'], 'diverged': True, 'message': tail}
     finally:
         sys.stdout = old_stdout
-        if quiet:
-            quiet.close()
     results = {k: v for k, v in results.items() if k in ('mae', 'accuracy', 'corr', 'mult_acc', 'f_score')}
     return {'config_num': cfg['config_num'], 'results': results, 'train_loss': train_losses[-1],
             'test_loss': test_losses[-1]}
@@ -220,10 +226,11 @@ def main(argv=None):
             with open(a.out, 'w') as f:
                 for r in out:
                     f.write(json.dumps(r) + '\n')
-        maes = [r['results'].get('mae', float('nan')) for r in out] if out and isinstance(out[0]['results'], dict) else []
+        maes = [r['results']['mae'] for r in out if 'results' in r]
         print(json.dumps({'metric': 'grid configs/s (e2e train + valid/test latents + sentiment regressor)',
                           'configs': len(out), 'n_gpus': world, 'seconds': dt, 'value': len(out) / dt,
                           'epochs_scale': a.epochs_scale, 'cuda_graph': not a.no_graph,
+                          'diverged': [r['config_num'] for r in out if r.get('diverged')],
                           'best_test_MAE': (min(maes) if maes else None)}), flush=True)
 
 
