@@ -203,6 +203,14 @@ def load_peaks():
         return 6650.0, 'fallback (B200_PROFILING.md: 6.65 TB/s)'
 
 
+def load_tensor_peak():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            return float(json.load(fh)['bf16_tflops'])
+    except Exception:
+        return 1590.0
+
+
 def load_traffic(n_local):
     """DRAM bytes per embed launch from the committed ncu capture, if it was taken at this size."""
     try:
@@ -359,7 +367,21 @@ def main():
     roofline = {'bound': 'hbm', 'kernel': 'sif_embed_warp_kernel<3,false>', 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': load_traffic(n_local),
                 'peak_source': peak_src, 'algorithmic_bytes_per_launch': n_local * EMBED_BYTES_PER_UTT,
-                'launch_ms': stage_ms['embed'], 'stage_ms': stage_ms}
+                'launch_ms': stage_ms['embed'], 'stage_ms': stage_ms,
+                # the other two streaming stages against their own bounds: the Gram's
+                # algorithmic 2 d^2 FLOP per utterance against half the measured bf16 GEMM rate (no TF32
+                # rate is measured on this pool; the 3xTF32 kernel executes 2.05x the algorithmic FLOPs),
+                # the projection's 2 d 4 bytes per utterance against the measured copy bandwidth
+                'other_stages': {
+                    'gram': {'bound': 'tensor', 'unit': 'TFLOP/s',
+                             'achieved': n_local * 2.0 * DIM * DIM / (stage_ms['gram'] * 1e-3) / 1e12,
+                             'peak': load_tensor_peak() / 2.0, 'peak_source': 'bf16_tflops / 2 (TF32, assumed)',
+                             'executed_over_algorithmic': 2.05},
+                    'project': {'bound': 'hbm', 'unit': 'GB/s',
+                                'achieved': n_local * 2.0 * DIM * 4 / (stage_ms['project'] * 1e-3) / 1e9,
+                                'peak': peak}}}
+    for _st in roofline['other_stages'].values():
+        _st['frac'] = _st['achieved'] / _st['peak']
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sample = int(os.environ.get('MMB_CPU_SAMPLE', 50_000))

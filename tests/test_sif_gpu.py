@@ -224,3 +224,48 @@ def test_gram_tcgen05_matches_float64(mods):
         assert torch.equal(G, sf.gram(X, nv.GRAM_TF32X3))            # deterministic
         G32 = sf.gram(X, nv.GRAM_FP32)
         assert (G - G32).abs().max().item() < 2e-5 * scale
+
+
+def test_peer_exchange_single_rank(mods):
+    """The NVLink exchange entry points with world = 1 (the multi-rank case is tools/dist_check.py
+    under torchrun, tests/test_dist_gpu.py): the stand-alone all-reduce is the identity, and the
+    fused Gram + exchange equals mmb_gram, on both Gram paths, over several epochs (slot parity)."""
+    import ctypes as C
+    import torch
+    nv, sf = mods[0], mods[1]
+    lib = nv.lib
+    dev = torch.device('cuda')
+    buf = C.c_void_p()
+    nv.check(lib.mmb_comm_alloc(C.byref(buf)))
+    try:
+        assert lib.mmb_comm_bytes() >= 2 * 300 * 300 * 4
+        handle = (C.c_char * 64)()
+        nv.check(lib.mmb_comm_export(buf, handle))
+        bufs = (C.c_void_p * 1)(buf.value)
+        st = torch.zeros(1, dtype=torch.int32, device=dev)
+        g = torch.Generator(device=dev).manual_seed(3)
+        epoch = 0
+        for n, dtype in ((90000, torch.float32), (3300, torch.float64), (7, torch.float32)):
+            x = torch.randn(n, device=dev, generator=g, dtype=dtype)
+            want = x.clone()
+            epoch += 1
+            nv.check(lib.mmb_allreduce_peer(nv.ptr(x), n, int(dtype == torch.float64), 0, 1, bufs,
+                                            C.c_uint64(epoch), nv.ptr(st), nv.stream_ptr()))
+            assert torch.equal(x, want)
+        for n in (157, 5000, 20000):
+            X = (0.4 * torch.randn(n, 300, device=dev, generator=g) + 0.3).contiguous()
+            want = sf.gram(X)
+            G = torch.empty((300, 300), device=dev)
+            nbytes = lib.mmb_gram_workspace_bytes(n, 300, 0)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            epoch += 1
+            nv.check(lib.mmb_gram_allreduce_peer(nv.ptr(X), n, 300, nv.ptr(G), nv.ptr(ws), nbytes, 0, 0, 1, bufs,
+                                                 C.c_uint64(epoch), nv.ptr(st), nv.stream_ptr()))
+            assert torch.equal(G, want), n
+        assert int(st.item()) == 0
+        with pytest.raises(ValueError):
+            nv.check(lib.mmb_allreduce_peer(nv.ptr(G), 90000, 0, 0, 1, bufs, C.c_uint64(0), nv.ptr(st),
+                                            nv.stream_ptr()))          # epoch must be > 0
+    finally:
+        torch.cuda.synchronize()
+        nv.check(lib.mmb_comm_free(buf))
