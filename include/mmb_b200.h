@@ -230,6 +230,22 @@ MMB_API int mmb_closed_form_finish(int N, int L, int d, const float* sent_w, con
                            const float* prod, const float* tw_part, int n_mod, float* out,
                            mmb_stream_t stream);
 
+/* ---------------------------------------------------------------- preprocessing (N3) */
+/* normalize_data utils.py:155-191 + add_positional_embeddings utils.py:130-153 + the mask
+ * extension of simplesif.py:369-375 on the device, for one feature tensor x (N, T, F_in) float32.
+ * mmb_feature_minmax: per-column min / max over all N*T rows (the split's own statistics).
+ * mmb_prep_features: keep[] (device, F_out ints, ascending) lists the non-constant source columns
+ * (max > min; the reference drops constant AUDIO features only -- pass all columns for the visual
+ * tensor); out / mask are (N, T, F_out + pos_embed_dim): value (x + min) * 2 / (max - min) - 1
+ * (the reference adds the minimum), exact zeros -> -10 with mask 0, then pos_embed_dim position
+ * columns with the reference's first-axis quirk and mask 1.                                 */
+MMB_API size_t mmb_feature_minmax_workspace_bytes(int64_t rows, int F);
+MMB_API int mmb_feature_minmax(const float* x, int64_t rows, int F, float* mn, float* mx, void* ws,
+                       size_t ws_bytes, mmb_stream_t stream);
+MMB_API int mmb_prep_features(const float* x, int64_t N, int T, int F_in, const int* keep, int F_out,
+                      int pos_embed_dim, const float* mn, const float* mx, float* out, float* mask,
+                      mmb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,9 @@ SIGNATURES = {
     'mmb_gauss_ll': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'mmb_closed_form_stats': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'mmb_closed_form_finish': (_i, [_i, _i, _i, _p, _p, _p, _p, _i, _p, _p]),
+    'mmb_feature_minmax_workspace_bytes': (_sz, [_i64, _i]),
+    'mmb_feature_minmax': (_i, [_p, _i64, _i, _p, _p, _p, _sz, _p]),
+    'mmb_prep_features': (_i, [_p, _i64, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p]),
     'mmb_row_inv_norm': (_i, [_p, _i64, _i, _p, _p]),
     'mmb_word_ll_workspace_bytes': (_sz, [_i, _i64, _i]),
     'mmb_word_ll': (_i, [_p, _i, _i, _p, _p, _i64, _p, _i64, _i64, _p, _p, _i64, _i64, _i, _f, _p, _p,

@@ -61,6 +61,47 @@ def normalize_data(train):
     return train, {'covarep': audio_mask, 'facet': vis_mask}
 
 
+def prep_features_device(x, pos_embed_dim=0, drop_constant=True, device=None):
+    """``normalize_data`` + ``add_positional_embeddings`` + the mask extension of reference
+    simplesif.py:369-375 for ONE raw feature tensor ``x`` (N, T, F), on the device (SURVEY.md §8f
+    N3, libmmb_b200 ``mmb_feature_minmax`` / ``mmb_prep_features``).  Returns ``(values, mask,
+    kept)``: float32 CUDA tensors of shape (N, T, F_kept + pos_embed_dim) as ``MMData`` stores them,
+    and the kept source columns.  ``drop_constant`` is the reference's rule for the audio tensor
+    (utils.py:163-168); the visual tensor keeps every column."""
+    import _native as nv
+    from _native import lib
+    device = device or nv.require_cuda()
+    x_t = nv.to_device(x, torch.float32, device)
+    N, T, F = x_t.shape
+    mn = torch.empty(F, dtype=torch.float32, device=device)
+    mx = torch.empty(F, dtype=torch.float32, device=device)
+    nbytes = lib.mmb_feature_minmax_workspace_bytes(N * T, F)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
+    nv.check(lib.mmb_feature_minmax(nv.ptr(x_t), N * T, F, nv.ptr(mn), nv.ptr(mx), nv.ptr(ws), nbytes,
+                                    nv.stream_ptr()))
+    if drop_constant:
+        kept = torch.nonzero(mx - mn, as_tuple=False).flatten().to(torch.int32)
+    else:
+        kept = torch.arange(F, dtype=torch.int32, device=device)
+    F_out = int(kept.numel())
+    if F_out == 0:
+        raise ValueError('every feature of the tensor is constant')
+    out = torch.empty((N, T, F_out + pos_embed_dim), dtype=torch.float32, device=device)
+    mask = torch.empty_like(out)
+    nv.check(lib.mmb_prep_features(nv.ptr(x_t), N, T, F, nv.ptr(kept.contiguous()), F_out, int(pos_embed_dim),
+                                   nv.ptr(mn), nv.ptr(mx), nv.ptr(out), nv.ptr(mask), nv.stream_ptr()))
+    return out, mask, kept
+
+
+def normalize_data_device(train, pos_embed_dim=0, device=None):
+    """Device counterpart of ``normalize_data`` (+ positional columns when ``pos_embed_dim`` > 0):
+    returns ``({'covarep': tensor, 'facet': tensor}, {'covarep': mask, 'facet': mask})`` as float32
+    CUDA tensors ready for ``MMData``; ``train`` is not modified."""
+    cov, cov_m, _ = prep_features_device(train['covarep'], pos_embed_dim, True, device)
+    fac, fac_m, _ = prep_features_device(train['facet'], pos_embed_dim, False, device)
+    return {'covarep': cov, 'facet': fac}, {'covarep': cov_m, 'facet': fac_m}
+
+
 def _as_f32(x, device):
     return x if torch.is_tensor(x) else torch.tensor(x, device=device, dtype=torch.float32)
 

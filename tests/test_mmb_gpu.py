@@ -268,3 +268,38 @@ def test_closed_form_estimate(mods, golden_dir, tag, segments):
     wm, wsg = mo.calc_weights(c['aud'], c['heads']['audio'][1], c['heads']['audio'][3])
     close(qm.detach().cpu(), wm, 1e-5, 'q_mean')
     close(qs.detach().cpu(), wsg, 1e-5, 'q_sigma')
+
+
+@pytest.mark.parametrize('pos', [0, 2, 4])
+def test_device_preprocessing_matches_reference(mods, golden_dir, pos):
+    """utils.normalize_data_device against the reference's normalize_data /
+    add_positional_embeddings outputs (golden utils.npz) and against this repo's NumPy drop-ins."""
+    torch, losses, models = mods
+    import utils
+    g = np.load(os.path.join(golden_dir, 'utils.npz'))
+    split = cases.raw_split()
+    data, masks = utils.normalize_data_device(split, pos_embed_dim=pos)
+    F_a, F_v = g['covarep'].shape[-1], g['facet'].shape[-1]
+    assert data['covarep'].shape == split['covarep'].shape[:2] + (F_a + pos,)
+    close(data['covarep'][..., :F_a].cpu(), g['covarep'], 2e-6, 'covarep')
+    close(data['facet'][..., :F_v].cpu(), g['facet'], 2e-6, 'facet')
+    np.testing.assert_array_equal(masks['covarep'][..., :F_a].cpu().numpy(), g['m_covarep'].astype(np.float32))
+    np.testing.assert_array_equal(masks['facet'][..., :F_v].cpu().numpy(), g['m_facet'].astype(np.float32))
+    if pos:
+        want = utils.add_positional_embeddings({'pos_embed_dim': pos}, np.zeros(split['covarep'].shape))[..., -pos:]
+        close(data['covarep'][..., F_a:].cpu(), want, 2e-6, 'positional columns')
+        close(data['facet'][..., F_v:].cpu(), want, 2e-6, 'positional columns (visual)')
+        assert bool((masks['covarep'][..., F_a:] == 1).all())
+    if pos == 4:
+        close(data['covarep'][..., F_a:].cpu(), g['pos'][..., -4:], 2e-6, 'positional vs reference golden')
+    # a larger random tensor against the NumPy drop-in
+    rng = np.random.default_rng(9)
+    big = {'covarep': rng.normal(size=(301, 20, 74)) * 2 + 1, 'facet': rng.normal(size=(301, 20, 47))}
+    big['covarep'][:, 15:, :] = 0
+    big['facet'][:, 15:, :] = 0
+    big['covarep'][:, :, 7] = 0
+    ref, ref_m = utils.normalize_data({k: v.copy() for k, v in big.items()})
+    dev, dev_m = utils.normalize_data_device(big, pos_embed_dim=0)
+    close(dev['covarep'].cpu(), ref['covarep'], 5e-6, 'big covarep')
+    close(dev['facet'].cpu(), ref['facet'], 5e-6, 'big facet')
+    np.testing.assert_array_equal(dev_m['covarep'].cpu().numpy(), ref_m['covarep'].astype(np.float32))
