@@ -183,6 +183,17 @@ MMB_API int mmb_heads_backward(const float* z, int B, int d, int n_heads, const 
                        const int* D, const float* const* gout, float* dz, float* const* dW,
                        float* const* db, void* ws, size_t ws_bytes, mmb_stream_t stream);
 
+/* Launch-count helpers of the step (B = 64: every torch element-wise op is a launch).
+ * mmb_scale_multi: out[i] (B, D[i]) = in[i] * row[i][b] * elem[i][b][f] for n <= 16 tensors in one
+ * launch (row / elem tables or entries may be NULL = 1): the chain rule through the per-modality
+ * log-likelihoods (12 multiplies per MMB2 step) and d sigma / d log_sigma = sigma (6 more).
+ * mmb_gather_multi: dst[i] (B, W[i]) = src[i][idx[b]] for n <= 16 row-major tensors sharing one
+ * int64 index vector: the batch tuple of MMData.__getitem__ (utils.py:231-233) in one launch.   */
+MMB_API int mmb_scale_multi(int n, int B, const int* D, const float* const* in, const float* const* row,
+                    const float* const* elem, float* const* out, mmb_stream_t stream);
+MMB_API int mmb_gather_multi(int n, int B, const int64_t* idx, const float* const* src, const int64_t* W,
+                     float* const* dst, mmb_stream_t stream);
+
 /* get_normal_log_prob -- losses.py:13-34 for n_mod modalities in ONE launch: value and the
  * analytic gradients.  Modality m is the concatenation along the
  * feature axis (the torch.cat of simplesif.py:94-113, never materialised) of n_seg[m]

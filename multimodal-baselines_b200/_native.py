@@ -57,6 +57,8 @@ SIGNATURES = {
     'mmb_heads_forward': (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     'mmb_heads_backward_workspace_bytes': (_sz, [_i, _i, _i, _p]),
     'mmb_heads_backward': (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    'mmb_scale_multi': (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
+    'mmb_gather_multi': (_i, [_i, _i, _p, _p, _p, _p, _p]),
     'mmb_gauss_ll': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'mmb_closed_form_stats': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'mmb_closed_form_finish': (_i, [_i, _i, _i, _p, _p, _p, _p, _i, _p, _p]),

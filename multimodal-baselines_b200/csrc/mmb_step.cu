@@ -94,6 +94,47 @@ struct DzItems {          // split-K work items of heads_bwd_dz: rows [k0, k0 + 
   int n_items;
 };
 
+// ---- multi-tensor helpers: the step is launch-bound, so chains of per-modality element-wise
+// ---- torch ops (12 + 6 multiplies in the backward pass, 8 batch gathers) become one launch each.
+constexpr int kMaxMulti = 16;
+struct ScaleArgs {
+  const float* in[kMaxMulti];     // (B, D[i])
+  const float* row[kMaxMulti];    // (B) row scale or null
+  const float* elem[kMaxMulti];   // (B, D[i]) element-wise factor or null
+  float* out[kMaxMulti];
+  int D[kMaxMulti];
+  int n;
+};
+// out[i][b][f] = in[i][b][f] * (row[i] ? row[i][b] : 1) * (elem[i] ? elem[i][b][f] : 1); grid (B, n)
+__global__ void __launch_bounds__(128) scale_multi_kernel(const __grid_constant__ ScaleArgs a) {
+  const int b = blockIdx.x, i = blockIdx.y, D = a.D[i];
+  const float r = a.row[i] ? __ldg(a.row[i] + b) : 1.f;
+  const float* in = a.in[i] + (size_t)b * D;
+  const float* el = a.elem[i] ? a.elem[i] + (size_t)b * D : nullptr;
+  float* out = a.out[i] + (size_t)b * D;
+  for (int f = threadIdx.x; f < D; f += blockDim.x) out[f] = in[f] * r * (el ? __ldg(el + f) : 1.f);
+}
+
+struct GatherArgs {
+  const float* src[kMaxMulti];    // (N_i, W[i]) row-major
+  float* dst[kMaxMulti];          // (B, W[i])
+  int64_t W[kMaxMulti];           // row width in floats (trailing dims flattened)
+  int n;
+};
+// dst[i][b][:] = src[i][idx[b]][:]; grid (B, n)
+__global__ void __launch_bounds__(256)
+    gather_multi_kernel(const __grid_constant__ GatherArgs a, const int64_t* __restrict__ idx) {
+  const int b = blockIdx.x, i = blockIdx.y;
+  const int64_t W = a.W[i];
+  const float* s = a.src[i] + (size_t)idx[b] * W;
+  float* d = a.dst[i] + (size_t)b * W;
+  if ((W & 3) == 0 && (((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+    for (int64_t k = threadIdx.x; k < (W >> 2); k += blockDim.x) ((float4*)d)[k] = __ldg((const float4*)s + k);
+  } else {
+    for (int64_t k = threadIdx.x; k < W; k += blockDim.x) d[k] = __ldg(s + k);
+  }
+}
+
 // ---------------------------------------------------------------- heads (A6) ---------
 struct HeadsArgs {
   const float* W[kMaxHeads];
@@ -223,7 +264,23 @@ __global__ void __launch_bounds__(128)
     const float mu = __ldg(args.mu[m] + (size_t)b * D + f);
     const float sg = __ldg(args.sigma[m] + (size_t)b * D + f);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int t = 0; t < T; ++t) {
+    int t = 0;
+    for (; t + 4 <= T; t += 4) {   // 8 independent loads in flight, then the (ordered) sums
+      float mk[4], xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        mk[u] = __ldg(k + (size_t)(t + u) * F);
+        xv[u] = __ldg(x + (size_t)(t + u) * F);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float df = xv[u] - mu;
+        s0 += mk[u];
+        s1 = fmaf(mk[u], df, s1);
+        s2 = fmaf(mk[u] * df, df, s2);
+      }
+    }
+    for (; t < T; ++t) {
       const float mk = __ldg(k + (size_t)t * F);
       const float df = __ldg(x + (size_t)t * F) - mu;
       s0 += mk;
@@ -487,6 +544,38 @@ extern "C" int mmb_heads_backward(const float* z, int B, int d, int n_heads, con
     heads_bwd_dw_kernel<<<grid, 256, 0, st>>>(z, B, d, a);
     MMB_LAUNCH_CHECK("heads_bwd_dw");
   }
+  return MMB_OK;
+}
+
+extern "C" int mmb_scale_multi(int n, int B, const int* D, const float* const* in, const float* const* row,
+                               const float* const* elem, float* const* out, mmb_stream_t stream) {
+  MMB_REQUIRE(D && in && out, "null pointer");
+  MMB_REQUIRE(n > 0 && n <= kMaxMulti && B > 0, "1..16 tensors");
+  ScaleArgs a = {};
+  for (int i = 0; i < n; ++i) {
+    MMB_REQUIRE(in[i] && out[i] && D[i] > 0, "null tensor");
+    a.in[i] = in[i]; a.out[i] = out[i]; a.D[i] = D[i];
+    a.row[i] = row ? row[i] : nullptr;
+    a.elem[i] = elem ? elem[i] : nullptr;
+  }
+  a.n = n;
+  scale_multi_kernel<<<dim3(B, n), 128, 0, as_stream(stream)>>>(a);
+  MMB_LAUNCH_CHECK("scale_multi");
+  return MMB_OK;
+}
+
+extern "C" int mmb_gather_multi(int n, int B, const int64_t* idx, const float* const* src, const int64_t* W,
+                                float* const* dst, mmb_stream_t stream) {
+  MMB_REQUIRE(idx && src && W && dst, "null pointer");
+  MMB_REQUIRE(n > 0 && n <= kMaxMulti && B > 0, "1..16 tensors");
+  GatherArgs a = {};
+  for (int i = 0; i < n; ++i) {
+    MMB_REQUIRE(src[i] && dst[i] && W[i] > 0, "null tensor");
+    a.src[i] = src[i]; a.dst[i] = dst[i]; a.W[i] = W[i];
+  }
+  a.n = n;
+  gather_multi_kernel<<<dim3(B, n), 256, 0, as_stream(stream)>>>(a, idx);
+  MMB_LAUNCH_CHECK("gather_multi");
   return MMB_OK;
 }
 

@@ -29,6 +29,32 @@ def _int_array(vals):
     return (C.c_int * len(vals))(*[int(v) for v in vals])
 
 
+def scale_multi(ins, rows=None, elems=None):
+    """out[i] = ins[i] * rows[i][:, None] * elems[i] for up to 16 (B, D_i) tensors in ONE launch
+    (``mmb_scale_multi``); ``rows`` / ``elems`` entries may be None."""
+    B = ins[0].shape[0]
+    outs = [torch.empty_like(t) for t in ins]
+    for lo in range(0, len(ins), 16):
+        sl = slice(lo, lo + 16)
+        nv.check(lib.mmb_scale_multi(len(ins[sl]), B, _int_array([t.shape[1] for t in ins[sl]]), _ptr_array(ins[sl]),
+                                     _ptr_array(rows[sl]) if rows is not None else None,
+                                     _ptr_array(elems[sl]) if elems is not None else None,
+                                     _ptr_array(outs[sl]), nv.stream_ptr()))
+    return outs
+
+
+def gather_multi(srcs, idx):
+    """[s[idx] for s in srcs] for float32 CUDA tensors sharing one int64 index vector, in ONE launch
+    (``mmb_gather_multi``): the batch tuple of ``MMData.__getitem__``."""
+    B = int(idx.shape[0])
+    srcs = [_f32(s) for s in srcs]
+    outs = [torch.empty((B,) + tuple(s.shape[1:]), dtype=torch.float32, device=s.device) for s in srcs]
+    W = (C.c_int64 * len(srcs))(*[int(s[0].numel()) for s in srcs])
+    nv.check(lib.mmb_gather_multi(len(srcs), B, nv.ptr(idx.contiguous()), _ptr_array(srcs), W, _ptr_array(outs),
+                                  nv.stream_ptr()))
+    return outs
+
+
 class HeadsFunction(torch.autograd.Function):
     """All (mu, log_sigma) heads of AudioVisualGeneratorMultimodal in one launch
     (reference models.py:196-202).  ``apply(z, is_log_sigma, W0, b0, W1, b1, ...)`` returns
@@ -56,13 +82,13 @@ class HeadsFunction(torch.autograd.Function):
         n = len(ctx.Ds)
         z, Ws, sig = saved[0], saved[1:1 + n], list(saved[1 + n:])
         B, d = z.shape
-        gpre = []
-        for h in range(n):
-            g = gouts[h]
-            g = torch.zeros((B, ctx.Ds[h]), dtype=torch.float32, device=z.device) if g is None else _f32(g)
-            if ctx.is_log_sigma[h]:
-                g = g * sig.pop(0)            # d sigma / d s = sigma  (sigma = exp(s))
-            gpre.append(g.contiguous())
+        gpre = [torch.zeros((B, ctx.Ds[h]), dtype=torch.float32, device=z.device) if gouts[h] is None
+                else _f32(gouts[h]) for h in range(n)]
+        ls = [h for h in range(n) if ctx.is_log_sigma[h]]
+        if ls:                                # d sigma / d s = sigma  (sigma = exp(s)): one launch
+            scaled = scale_multi([gpre[h] for h in ls], None, list(sig))
+            for h, g in zip(ls, scaled):
+                gpre[h] = g
         need_z = ctx.needs_input_grad[0]
         need_w = any(ctx.needs_input_grad[2:])
         dz = torch.empty_like(z) if need_z else None
@@ -128,11 +154,12 @@ class GaussLLFunction(torch.autograd.Function):
     def backward(ctx, g):
         n = ctx.n_mod
         dmu, dsg = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        g = _f32(g)
+        scaled = scale_multi(list(dmu) + list(dsg), [g[m] for m in range(n)] * 2, None)   # chain rule, one launch
         grads = [None, None]
         for m in range(n):
-            gm = g[m].unsqueeze(1)
-            grads.append(gm * dmu[m] if ctx.needs_input_grad[2 + 2 * m] else None)
-            grads.append(gm * dsg[m] if ctx.needs_input_grad[3 + 2 * m] else None)
+            grads.append(scaled[m] if ctx.needs_input_grad[2 + 2 * m] else None)
+            grads.append(scaled[n + m] if ctx.needs_input_grad[3 + 2 * m] else None)
         return tuple(grads)
 
 

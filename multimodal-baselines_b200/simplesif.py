@@ -117,8 +117,16 @@ class GraphedStep(object):
         self.graphs = {}
         self.mmb_ops = mmb_ops
 
+    def _gather(self, j):
+        """``dataset[j]`` (reference utils.py:231-233 / 248-251) as one multi-tensor gather launch."""
+        ds = self.dataset
+        names = ['text', 'audio', 'visual', 'text_mask', 'audio_mask', 'visual_mask', 'text_weights']
+        if hasattr(ds, 'text_aligned'):
+            names += ['text_aligned', 'text_aligned_mask']
+        return (j,) + tuple(self.mmb_ops.gather_multi([getattr(ds, n) for n in names], j))
+
     def _step(self, j):
-        x = self.dataset[j]                       # batched gather of the device-resident tensors
+        x = self._gather(j)                       # batched gather of the device-resident tensors
         _, batch_data, batch_masks = _batch_dicts(self.args, x)
         e = self.embeddings[j]
         out = self.gen_model(e)

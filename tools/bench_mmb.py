@@ -100,7 +100,7 @@ def ours_step(model, e, batch, word_fn, losses):
     return losses.get_log_prob_matrix({}, e, out, data, masks, word_fn, device=e.device)
 
 
-def run(name, steps, do_cpu):
+def run(name, steps, do_cpu, only_ours=False):
     import losses
     import models
     import simplesif
@@ -146,6 +146,9 @@ def run(name, steps, do_cpu):
 
     ours = make_loop(lambda m, e, b: ours_step(m, e, b, word_fn, losses), dev)
     ms_ours, l_ours = time_gpu(ours, steps)
+    if only_ours:
+        print(json.dumps({'shape': name, 'b200_fused': {'ms_per_step': ms_ours}}))
+        return
     # the same step replayed as one captured CUDA graph (simplesif.GraphedStep)
     import utils
     ds = utils.MMData(S['text'], S['aud'], S['vis'], {'text': S['text_m'], 'covarep': S['aud_m'], 'facet': S['vis_m']},
@@ -180,6 +183,7 @@ if __name__ == '__main__':
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--shape', default='both')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--only-eager-ours', action='store_true', help='profiling aid: only the eager fused arm')
     a = ap.parse_args()
     for nm in (['mosi', 'pom'] if a.shape == 'both' else [a.shape]):
-        run(nm, a.steps, not a.no_cpu)
+        run(nm, a.steps, not a.no_cpu, a.only_eager_ours)
