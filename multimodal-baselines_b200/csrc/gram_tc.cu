@@ -10,8 +10,11 @@
 //              UMMA LayoutType 1, cute Swizzle<2,5,2>; the only MN-major layout tf32 accepts).
 //              X is row-major (N, 300), i.e. "MN-major" for both operands of X^T X, so no
 //              transpose is ever needed: A = B = the same shared-memory tile.  5-stage ring.
-//   workers  : 4 warps compute lo = x - trunc_tf32(x) into a second buffer (element-wise, so
-//              swizzle-agnostic).  The MMA ignores the low 13 mantissa bits of its FP32
+//   workers  : 4 "split" warps compute lo = x - trunc_tf32(x) into a second buffer (element-wise,
+//              so swizzle-agnostic) and drain TMEM at segment ends; 4 "corner" warps compute
+//              block C (below).  Keeping the two jobs on separate warps matters: on one set of
+//              warps their per-stage work was as long as the MMAs of the stage, so the tensor
+//              pipe idled whenever a flush put the workers behind.  The MMA ignores the low 13 mantissa bits of its FP32
 //              operands (verified bit-for-bit on B200), so "hi" is the raw TMA tile.
 //   MMA      : one elected thread issues tcgen05.mma (M = 128) for the upper-triangular blocks
 //                 tile A  rows   0..127 x cols   0..303   (N = 256 + 48)   TMEM cols   0..303
@@ -46,7 +49,7 @@ constexpr int kHiBytes = kBoxes * kBoxBytes;    // 20480
 constexpr int kStageBytes = 2 * kHiBytes;       // hi + lo
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int kSegDefault = 64;                 // 1024 rows between TMEM flushes
-constexpr int kThreads = 192;                   // warp0 TMA, warp1 MMA, warps 2-5 split/epilogue
+constexpr int kThreads = 320;                   // warp0 TMA, warp1 MMA, warps 2-5 split + TMEM flush, warps 6-9 corner block
 constexpr int kColsAB = 480, kColsC = 48;
 constexpr int kPartialStride = 128 * kColsAB + kColsC * kColsC;   // floats per CTA: tiles A|B, then block C
 
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_ready + 8 * s, 4);
-      mbar_init(bar_empty + 8 * s, 5);   // MMA commit + the four worker warps (block C reads)
+      mbar_init(bar_empty + 8 * s, 5);   // MMA commit + the four corner warps (block C reads)
     }
     mbar_init(bar_done, 1);
     mbar_init(bar_free, 4);
@@ -223,32 +226,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         umma_commit(bar_done);              // this segment's accumulators are complete
       }
     }
-  } else {
-    // ===== workers: lo = x - trunc_tf32(x); block C (rows/cols 256..299) in FP32; flushes =====
+  } else if (warp < 6) {
+    // ===== split warps: lo = x - trunc_tf32(x) for every stage; TMEM flush at segment ends =====
     const int t = threadIdx.x - 64;  // 0..127
     const int q = warp & 3;          // TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;
     float* part = prm.partial + (size_t)blockIdx.x * kPartialStride;
     float* outT = part + row;   // column-major tiles A|B: element (row, c) at part[c * 128 + row]
-    // block C: 11 x 11 grid of 4x4 blocks over cols 256..299, upper triangle (66 pairs),
-    // dealt round-robin to the four warps.
-    const int pidx = lane * 4 + (warp - 2);
-    int ti = 0, tj = 0;
-    const bool has_c = pidx < 66;
-    if (has_c) {
-      int r = pidx;
-      while (r >= 11 - ti) { r -= 11 - ti; ++ti; }
-      tj = ti + r;
-    }
-    float cacc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) cacc[a][b] = 0.f;
-    const int ca = 4 * ti, cb = 4 * tj;   // column offsets inside [256, 300)
-    const uint32_t offa = (8 + (ca >> 5)) * kBoxBytes + (ca & 7) * 4, cha = (ca & 31) >> 3;
-    const uint32_t offb = (8 + (cb >> 5)) * kBoxBytes + (cb & 7) * 4, chb = (cb & 31) >> 3;
-
     int64_t i = 0;
     for (int64_t sg = 0; sg < nseg; ++sg) {
       int64_t iend = i + prm.seg;
@@ -273,28 +257,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_ready + 8 * s);
-        if (has_c) {
-#pragma unroll
-          for (int k = 0; k < kBK; ++k) {
-            // 32-byte chunk index is XOR-swizzled with (row & 3)  (SWIZZLE_128B_ATOM_32B)
-            const float4 a = *(const float4*)(stage + offa + k * 128 + ((cha ^ (k & 3)) << 5));
-            const float4 b = *(const float4*)(stage + offb + k * 128 + ((chb ^ (k & 3)) << 5));
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-              for (int v = 0; v < 4; ++v) cacc[u][v] = fmaf(av[u], bv[v], cacc[u][v]);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
       }
-      // flush this segment's TMEM accumulators into the FP32 partial (round-to-nearest adds)
-      mbar_wait(bar_done, (uint32_t)(sg & 1));
-      tc_fence_after();
+      // flush this segment's TMEM accumulators into the FP32 partial (round-to-nearest adds).
       // The partial is stored column-major (column c of tiles A|B = 128 consecutive floats), so
       // with lane = TMEM lane = tile row every global access of the read-modify-write is one
       // fully coalesced 128-byte line per warp (a row-major partial costs 32 lines per access).
+      mbar_wait(bar_done, (uint32_t)(sg & 1));
+      tc_fence_after();
       for (int c = 0; c < kColsAB; c += 32) {
         float* o = outT + (size_t)c * 128;
         float old[32];
@@ -318,6 +287,47 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     if (nseg == 0)
       for (int c = 0; c < kColsAB; ++c) outT[(size_t)c * 128] = 0.f;
+  } else {
+    // ===== corner warps: block C (rows/cols 256..299, does not fit in TMEM) in exact FP32 from the
+    // raw tile; 11 x 11 grid of 4x4 blocks, upper triangle (66 pairs), dealt round-robin =====
+    float* part = prm.partial + (size_t)blockIdx.x * kPartialStride;
+    const int pidx = lane * 4 + (warp - 6);
+    int ti = 0, tj = 0;
+    const bool has_c = pidx < 66;
+    if (has_c) {
+      int r = pidx;
+      while (r >= 11 - ti) { r -= 11 - ti; ++ti; }
+      tj = ti + r;
+    }
+    float cacc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) cacc[a][b] = 0.f;
+    const int ca = 4 * ti, cb = 4 * tj;   // column offsets inside [256, 300)
+    const uint32_t offa = (8 + (ca >> 5)) * kBoxBytes + (ca & 7) * 4, cha = (ca & 31) >> 3;
+    const uint32_t offb = (8 + (cb >> 5)) * kBoxBytes + (cb & 7) * 4, chb = (cb & 31) >> 3;
+    for (int64_t i = 0; i < nkb; ++i) {
+      const int s = (int)(i % kStages);
+      const uint32_t ph = (uint32_t)((i / kStages) & 1);
+      mbar_wait(bar_full + 8 * s, ph);
+      const uint8_t* stage = smem + s * kStageBytes;
+      if (has_c) {
+#pragma unroll
+        for (int k = 0; k < kBK; ++k) {
+          // 32-byte chunk index is XOR-swizzled with (row & 3)  (SWIZZLE_128B_ATOM_32B)
+          const float4 a = *(const float4*)(stage + offa + k * 128 + ((cha ^ (k & 3)) << 5));
+          const float4 b = *(const float4*)(stage + offb + k * 128 + ((chb ^ (k & 3)) << 5));
+          const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) cacc[u][v] = fmaf(av[u], bv[v], cacc[u][v]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    }
     if (has_c) {
       float* cpart = part + 128 * kColsAB;   // 48 x 48 block-C region
 #pragma unroll
