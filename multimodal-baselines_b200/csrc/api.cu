@@ -52,6 +52,11 @@ static int resolve_gram_mode(int64_t N, int d, int mode) {
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+__global__ void accumulate_kernel(float* __restrict__ acc, const float* __restrict__ x, int n, int first) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) acc[i] = first ? x[i] : acc[i] + x[i];
+}
+
 __global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restrict__ out, int64_t n) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
@@ -233,7 +238,8 @@ extern "C" int mmb_sif_embedding_host(const float* table_dev, int64_t V, int d, 
   Streams S;
   int rc = S.init();
   if (rc) return rc;
-  DevBuf ids[2], emb, ws, omega, status, pcv, f64[2];
+  DevBuf ids[2], emb, ws, omega, status, pcv, f64[2], gchunk;
+  const bool chunked_gram = npc > 0 && nchunks > 1;
   const size_t ids_chunk = (size_t)chunk_rows * L * sizeof(int64_t);
   if ((rc = ids[0].alloc(ids_chunk, S.comp))) return rc;
   if ((rc = ids[1].alloc(ids_chunk, S.comp))) return rc;
@@ -246,6 +252,7 @@ extern "C" int mmb_sif_embedding_host(const float* table_dev, int64_t V, int d, 
     if ((rc = ws.alloc(ws_bytes, S.comp))) return rc;
     if ((rc = omega.alloc((size_t)orows * k * sizeof(double), S.comp))) return rc;
     if ((rc = pcv.alloc((size_t)npc * d * sizeof(float), S.comp))) return rc;
+    if (chunked_gram && (rc = gchunk.alloc((size_t)d * d * sizeof(float), S.comp))) return rc;
     MMB_CUDA(cudaMemcpyAsync(omega.p, Omega_host, (size_t)orows * k * sizeof(double),
                              cudaMemcpyHostToDevice, S.comp));
   }
@@ -279,15 +286,30 @@ extern "C" int mmb_sif_embedding_host(const float* table_dev, int64_t V, int d, 
                        (float*)emb.p + r0 * d, (int*)status.p, S.comp);
     if (rc) return rc;
     MMB_CUDA(cudaEventRecord(buf_free[b], S.comp));
+    if (chunked_gram) {
+      // The compute stream idles while the next chunk's ids cross PCIe: take the chunk's Gram now
+      // and add it to the running sum (chunk order -> deterministic), so that only the component
+      // solve separates the last H2D from the first D2H.
+      SifWs Lw = sif_ws_layout(N, d, npc);
+      char* base = (char*)ws.p;
+      float* G = (float*)(base + Lw.G);
+      rc = mmb_gram((const float*)emb.p + r0 * d, rows, d, (float*)gchunk.p, base + Lw.gram, Lw.pc - Lw.gram,
+                    gram_mode, S.comp);
+      if (rc) return rc;
+      accumulate_kernel<<<(d * d + 255) / 256, 256, 0, S.comp>>>(G, (const float*)gchunk.p, d * d, c == 0);
+      MMB_LAUNCH_CHECK("accumulate");
+    }
   }
-  // phase 2: Gram + components on the whole block, then projection chunk by chunk
+  // phase 2: components from the Gram of the whole block (summed per chunk above, or taken here)
   float* pc_dev = (float*)pcv.p;
   if (npc > 0) {
     SifWs Lw = sif_ws_layout(N, d, npc);
     char* base = (char*)ws.p;
     float* G = (float*)(base + Lw.G);
-    rc = mmb_gram((const float*)emb.p, N, d, G, base + Lw.gram, Lw.pc - Lw.gram, gram_mode, S.comp);
-    if (rc) return rc;
+    if (!chunked_gram) {
+      rc = mmb_gram((const float*)emb.p, N, d, G, base + Lw.gram, Lw.pc - Lw.gram, gram_mode, S.comp);
+      if (rc) return rc;
+    }
     const double* S0 = (const double*)omega.p;
     const int transposed = N < d;
     if (transposed) {

@@ -269,3 +269,31 @@ def test_peer_exchange_single_rank(mods):
     finally:
         torch.cuda.synchronize()
         nv.check(lib.mmb_comm_free(buf))
+
+
+@pytest.mark.parametrize('chunk_rows', [0, 700, 4096])
+def test_host_buffer_api_chunked(mods, chunk_rows):
+    """mmb_sif_embedding_host (pinned ids in, embeddings out) with several chunk sizes: the chunked
+    pipeline (per-chunk Gram summed in chunk order, projection overlapped with the D2H) gives the
+    device-resident result up to the FP32 order of the Gram sum, in float32 and float64 output."""
+    import torch
+    nv, sf = mods[0], mods[1]
+    lib = nv.lib
+    dev = torch.device('cuda')
+    rng = np.random.default_rng(17)
+    V, d, n, L = 5000, 300, 9001, 24
+    We = cases.table(V, d, 5)
+    ids, p = cases.zipf_ids(rng, n, L, V)
+    vw = np.concatenate([[1.0], 1e-3 / (1e-3 + p)]).astype(np.float32)
+    t_We, t_vw, t_ids = torch.tensor(We, device=dev), torch.tensor(vw, device=dev), torch.tensor(ids, device=dev)
+    want, pc_want = sf.sif_embedding_device(t_We, t_vw, t_ids, npc=1, return_pc=True)
+    omega = np.ascontiguousarray(sf.start_block(d, 1))
+    ids_c = np.ascontiguousarray(ids, dtype=np.int64)
+    for f64 in (0, 1):
+        out = np.empty((n, d), dtype=np.float64 if f64 else np.float32)
+        pc = np.empty((1, d), dtype=np.float32)
+        nv.check(lib.mmb_sif_embedding_host(nv.ptr(t_We), V, d, nv.ptr(t_vw), nv.np_ptr(ids_c), n, L, 1,
+                                            nv.np_ptr(omega), nv.np_ptr(out), f64, nv.np_ptr(pc), nv.GRAM_AUTO,
+                                            chunk_rows))
+        assert abs_cos(pc[0], pc_want[0].cpu().numpy()) > 1 - 1e-9
+        assert rel_err(out, want.cpu().numpy().astype(out.dtype)) < 2e-6
