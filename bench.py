@@ -334,6 +334,8 @@ def main():
                 nv.check(lib.mmb_sif_embedding_host(nv.ptr(table), VOCAB, DIM, nv.ptr(vocab_w),
                                                     nv.np_ptr(h_ids.array), n_local, L_TOK, 1, nv.np_ptr(omega),
                                                     nv.np_ptr(h_out.array), 0, None, nv.GRAM_AUTO, 0))
+            elif mdist.default_comm() is not None and N_UTT >= DIM:
+                mdist.default_comm().sif_embedding_host(table, vocab_w, h_ids.array, h_out.array, N_UTT, npc=1)
             else:
                 d_ids = torch.as_tensor(h_ids.array).to(dev, non_blocking=True)
                 e, _pc, _st = mdist.sharded_sif_embedding(table, vocab_w, d_ids, N_UTT, lo, npc=1)
@@ -356,7 +358,9 @@ def main():
                'h2d_bytes_per_step': int(N_UTT) * L_TOK * 8, 'd2h_bytes_per_step': int(N_UTT) * DIM * 4,
                'ms_per_step': float(dt.item()) * 1e3, 'steps': n_e2e,
                'api': 'mmb_sif_embedding_host (C ABI, pinned host buffers, float32 out)' if world == 1 else
-                      'pinned ids -> dist.sharded_sif_embedding -> pinned float32 out, per rank'}
+                      ('mmb_sif_embedding_host_peer (C ABI, pinned host buffers per rank, Gram summed over NVLink)'
+                       if mdist.default_comm() is not None else
+                       'pinned ids -> dist.sharded_sif_embedding -> pinned float32 out, per rank')}
         h_ids.free()
         h_out.free()
 

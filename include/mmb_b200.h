@@ -43,7 +43,8 @@ enum {
   MMB_E_INVALID = 1,     /* bad argument (null pointer, unsupported size)            */
   MMB_E_CUDA = 2,        /* a CUDA runtime call failed; see mmb_last_error()         */
   MMB_E_UNSUPPORTED = 3, /* valid request this build / device cannot run             */
-  MMB_E_INDEX = 4        /* token id outside [-V, V): the reference's IndexError      */
+  MMB_E_INDEX = 4,       /* token id outside [-V, V): the reference's IndexError      */
+  MMB_E_COMM = 5         /* a peer rank never arrived in a *_peer call (timeout)      */
 };
 
 enum {
@@ -160,6 +161,16 @@ MMB_API int mmb_allreduce_peer(void* x, int64_t n, int is_f64, int rank, int wor
 MMB_API int mmb_gram_allreduce_peer(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_bytes,
                                     int mode, int rank, int world, void* const* bufs, uint64_t epoch,
                                     int* status, mmb_stream_t stream);
+
+/* mmb_sif_embedding_host for one rank's block of a split of N_global utterances (N_global >= d):
+ * the same chunked H2D / embed / Gram pipeline, then the sum of the ranks' Grams over NVLink peer
+ * memory (mmb_allreduce_peer on the running sum), the replicated solve and the projection
+ * overlapped with the D2H.  All ranks call it with the same epoch; N_local may be 0.           */
+MMB_API int mmb_sif_embedding_host_peer(const float* table_dev, int64_t V, int d, const float* vocab_w_dev,
+                                const int64_t* x_host, int64_t N_local, int64_t L, int npc,
+                                const double* Omega_host, void* emb_host, int emb_f64, float* pc_host,
+                                int gram_mode, int64_t chunk_rows, int64_t N_global, int rank, int world,
+                                void* const* bufs, uint64_t epoch);
 
 /* ---------------------------------------------------------------- MMB (A6-A9) ----- */
 /* In this section the pointer tables (W, b, out, seg_val ...) are HOST arrays of DEVICE

@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libmmb_b200.so')
 
-MMB_OK, MMB_E_INVALID, MMB_E_CUDA, MMB_E_UNSUPPORTED, MMB_E_INDEX = 0, 1, 2, 3, 4
+MMB_OK, MMB_E_INVALID, MMB_E_CUDA, MMB_E_UNSUPPORTED, MMB_E_INDEX, MMB_E_COMM = 0, 1, 2, 3, 4, 5
 STATUS_BAD_INDEX, STATUS_NONFINITE, STATUS_COMM_TIMEOUT = 1, 2, 4
 GRAM_AUTO, GRAM_FP32, GRAM_TF32X3 = 0, 1, 2
 
@@ -46,6 +46,8 @@ SIGNATURES = {
     'mmb_sif_workspace_bytes': (_sz, [_i64, _i, _i]),
     'mmb_sif_embedding': (_i, [_p, _i64, _i, _p, _p, _i64, _i64, _i, _p, _p, _p, _p, _p, _sz, _i, _p, _p]),
     'mmb_sif_embedding_host': (_i, [_p, _i64, _i, _p, _p, _i64, _i64, _i, _p, _p, _i, _p, _i, _i64]),
+    'mmb_sif_embedding_host_peer': (_i, [_p, _i64, _i, _p, _p, _i64, _i64, _i, _p, _p, _i, _p, _i, _i64, _i64, _i, _i,
+                                         _p, C.c_uint64]),
     'mmb_comm_bytes': (_sz, []),
     'mmb_comm_alloc': (_i, [C.POINTER(_p)]),
     'mmb_comm_free': (_i, [_p]),

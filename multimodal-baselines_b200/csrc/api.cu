@@ -213,17 +213,28 @@ struct Streams {
 };
 }  // namespace
 
-extern "C" int mmb_sif_embedding_host(const float* table_dev, int64_t V, int d, const float* vocab_w_dev,
-                                      const int64_t* x_host, int64_t N, int64_t L, int npc,
-                                      const double* Omega_host, void* emb_host, int emb_f64,
-                                      float* pc_host, int gram_mode, int64_t chunk_rows) {
-  MMB_REQUIRE(table_dev && vocab_w_dev && x_host && emb_host, "null pointer");
+// Exchange parameters of the multi-GPU variant (world == 1: no exchange).
+struct HostComm {
+  int rank = 0, world = 1;
+  void* const* bufs = nullptr;
+  uint64_t epoch = 0;
+  int64_t n_global = 0;
+};
+
+static int sif_embedding_host_impl(const float* table_dev, int64_t V, int d, const float* vocab_w_dev,
+                                   const int64_t* x_host, int64_t N, int64_t L, int npc,
+                                   const double* Omega_host, void* emb_host, int emb_f64,
+                                   float* pc_host, int gram_mode, int64_t chunk_rows, const HostComm& hc) {
+  MMB_REQUIRE(table_dev && vocab_w_dev && (x_host || N == 0) && (emb_host || N == 0), "null pointer");
   MMB_REQUIRE(N >= 0 && L >= 0 && d > 0 && d % 4 == 0, "bad size");
   MMB_REQUIRE(npc >= 0 && npc + 10 <= 32, "npc must be in [0, 22]");
   MMB_REQUIRE(npc == 0 || Omega_host, "Omega is required when npc > 0");
-  if (N == 0) return MMB_OK;
+  const bool dist = hc.world > 1;
+  const int64_t n_global = dist ? hc.n_global : N;
+  MMB_REQUIRE(!dist || n_global >= d, "the multi-GPU host path needs N_global >= d (use sif_dist for tiny splits)");
+  if (N == 0 && !(dist && npc > 0)) return MMB_OK;
   if (chunk_rows <= 0) chunk_rows = 1 << 18;
-  if (chunk_rows > N) chunk_rows = N;
+  if (chunk_rows > N) chunk_rows = N > 0 ? N : 1;
   const int64_t nchunks = ceil_div(N, chunk_rows);
   const int k = npc + 10;
 
@@ -243,12 +254,12 @@ extern "C" int mmb_sif_embedding_host(const float* table_dev, int64_t V, int d, 
   const size_t ids_chunk = (size_t)chunk_rows * L * sizeof(int64_t);
   if ((rc = ids[0].alloc(ids_chunk, S.comp))) return rc;
   if ((rc = ids[1].alloc(ids_chunk, S.comp))) return rc;
-  if ((rc = emb.alloc((size_t)N * d * sizeof(float), S.comp))) return rc;
+  if ((rc = emb.alloc((size_t)(N > 0 ? N : 1) * d * sizeof(float), S.comp))) return rc;
   if ((rc = status.alloc(sizeof(int), S.comp))) return rc;
   MMB_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), S.comp));
-  const size_t ws_bytes = mmb_sif_workspace_bytes(N, d, npc);
+  const size_t ws_bytes = mmb_sif_workspace_bytes(N > 0 ? N : 1, d, npc);
   if (npc > 0) {
-    const int64_t orows = N >= d ? d : N;
+    const int64_t orows = n_global >= d ? d : N;
     if ((rc = ws.alloc(ws_bytes, S.comp))) return rc;
     if ((rc = omega.alloc((size_t)orows * k * sizeof(double), S.comp))) return rc;
     if ((rc = pcv.alloc((size_t)npc * d * sizeof(float), S.comp))) return rc;
@@ -303,15 +314,24 @@ extern "C" int mmb_sif_embedding_host(const float* table_dev, int64_t V, int d, 
   // phase 2: components from the Gram of the whole block (summed per chunk above, or taken here)
   float* pc_dev = (float*)pcv.p;
   if (npc > 0) {
-    SifWs Lw = sif_ws_layout(N, d, npc);
+    SifWs Lw = sif_ws_layout(N > 0 ? N : 1, d, npc);
     char* base = (char*)ws.p;
     float* G = (float*)(base + Lw.G);
     if (!chunked_gram) {
-      rc = mmb_gram((const float*)emb.p, N, d, G, base + Lw.gram, Lw.pc - Lw.gram, gram_mode, S.comp);
+      if (N > 0) {
+        rc = mmb_gram((const float*)emb.p, N, d, G, base + Lw.gram, Lw.pc - Lw.gram, gram_mode, S.comp);
+        if (rc) return rc;
+      } else {
+        MMB_CUDA(cudaMemsetAsync(G, 0, (size_t)d * d * sizeof(float), S.comp));
+      }
+    }
+    if (dist) {   // sum of the ranks' Grams over NVLink peer memory, rank order -> identical bits
+      rc = mmb_allreduce_peer(G, (int64_t)d * d, 0, hc.rank, hc.world, hc.bufs, hc.epoch, (int*)status.p,
+                              (mmb_stream_t)S.comp);
       if (rc) return rc;
     }
     const double* S0 = (const double*)omega.p;
-    const int transposed = N < d;
+    const int transposed = n_global < d;
     if (transposed) {
       rc = mmb_start_block_xt((const float*)emb.p, N, d, (const double*)omega.p, k,
                               (double*)(base + Lw.s0), S.comp);
@@ -361,9 +381,34 @@ extern "C" int mmb_sif_embedding_host(const float* table_dev, int64_t V, int d, 
   MMB_CUDA(cudaStreamSynchronize(S.comp));
   MMB_CUDA(cudaStreamSynchronize(S.out));
   MMB_CUDA(cudaStreamSynchronize(S.in));
+  if (h_status & MMB_STATUS_COMM_TIMEOUT) {
+    set_error("peer all-reduce timed out: a rank never raised its flag");
+    return MMB_E_COMM;
+  }
   if (h_status & MMB_STATUS_BAD_INDEX) {
     set_error("index out of bounds: a token id is outside [-%lld, %lld)", (long long)V, (long long)V);
     return MMB_E_INDEX;
   }
   return MMB_OK;
+}
+
+extern "C" int mmb_sif_embedding_host(const float* table_dev, int64_t V, int d, const float* vocab_w_dev,
+                                      const int64_t* x_host, int64_t N, int64_t L, int npc,
+                                      const double* Omega_host, void* emb_host, int emb_f64,
+                                      float* pc_host, int gram_mode, int64_t chunk_rows) {
+  return sif_embedding_host_impl(table_dev, V, d, vocab_w_dev, x_host, N, L, npc, Omega_host, emb_host, emb_f64,
+                                 pc_host, gram_mode, chunk_rows, HostComm());
+}
+
+extern "C" int mmb_sif_embedding_host_peer(const float* table_dev, int64_t V, int d, const float* vocab_w_dev,
+                                           const int64_t* x_host, int64_t N_local, int64_t L, int npc,
+                                           const double* Omega_host, void* emb_host, int emb_f64,
+                                           float* pc_host, int gram_mode, int64_t chunk_rows, int64_t N_global,
+                                           int rank, int world, void* const* bufs, uint64_t epoch) {
+  MMB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank / world");
+  MMB_REQUIRE(world == 1 || (bufs && epoch > 0), "exchange buffers and epoch > 0 are required");
+  HostComm hc;
+  hc.rank = rank; hc.world = world; hc.bufs = bufs; hc.epoch = epoch; hc.n_global = N_global;
+  return sif_embedding_host_impl(table_dev, V, d, vocab_w_dev, x_host, N_local, L, npc, Omega_host, emb_host,
+                                 emb_f64, pc_host, gram_mode, chunk_rows, hc);
 }

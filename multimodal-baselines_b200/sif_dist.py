@@ -108,6 +108,23 @@ class PeerComm(object):
                                                   nv.stream_ptr()))
         return G
 
+    def sif_embedding_host(self, table_t, vocab_w_t, ids_host, out_host, n_global, npc=1, gram_mode=0,
+                           chunk_rows=0):
+        """This rank's block through the host-buffer pipeline (``mmb_sif_embedding_host_peer``):
+        ``ids_host`` (n_local, L) int64 and ``out_host`` (n_local, d) float32/float64 are NumPy
+        arrays (pinned for full PCIe rate); H2D, embed and per-chunk Gram overlap, the Gram is summed
+        over the ranks through NVLink peer memory, the projection overlaps the D2H.  Synchronous."""
+        import sif_functions as sf
+        nv = self.nv
+        n_local, L = ids_host.shape
+        V, d = table_t.shape
+        omega = np.ascontiguousarray(sf.start_block(d, npc))
+        nv.check(self.lib.mmb_sif_embedding_host_peer(
+            nv.ptr(table_t), V, d, nv.ptr(vocab_w_t), nv.np_ptr(ids_host), n_local, L, npc, nv.np_ptr(omega),
+            nv.np_ptr(out_host), int(out_host.dtype == np.float64), None, gram_mode, chunk_rows, int(n_global),
+            self.rank, self.world, self.bufs, self._next()))
+        return out_host
+
     def check(self):
         """Synchronises; raises if a peer never arrived."""
         if int(self.status.item()) & self.nv.STATUS_COMM_TIMEOUT:
