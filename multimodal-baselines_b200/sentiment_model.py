@@ -1,8 +1,16 @@
 """Downstream sentiment regressor (reference sentiment_model.py).
 
-Outside the hot path by the task's own scope ("unchanged, only used for parity checks"): a
-small PyTorch MLP trained with L1 loss on fixed latents.  Same class / function names as the
-reference so that ``simplesif`` keeps its imports; no custom kernels here.
+Outside the hot path by the task's own scope ("unchanged, only used for parity checks"): a small
+PyTorch MLP trained with L1 loss on fixed latents, no custom kernels.  Same names, argument order,
+training schedule, files written and -- because the downstream metrics are compared with the
+reference's to the third decimal (tests/test_mmb_gpu.py::test_downstream_metrics) -- the same
+consumption of torch's global random stream: three shuffled loaders of batch 32, an initial pass
+over the test loader, a pass over the validation loader every ``valid_niter`` epochs whether or not
+early stopping is on.
+
+Two things differ in mechanism, not in result: batches are taken as index vectors from the
+DataLoader's own batch sampler (same draws, no per-sample collation of device scalars), and with
+``args['cuda_graph']`` each SGD step is one CUDA-graph replay.
 """
 import json
 import os
@@ -44,16 +52,48 @@ class SentimentModel(nn.Module):
         return self.out(F.relu(self.hidden1(inputs))).squeeze()
 
 
+def save_sentiment(path, model):
+    """reference sentiment_model.py:43-44."""
+    torch.save(model.state_dict(), os.path.join(path, 'senti.bin'))
+
+
+def load_sentiment(path, embedding_dim, hidden_dim, device, n_out=1):
+    """reference sentiment_model.py:46-50 (which omits ``n_out`` and cannot run; only ever bound in an
+    unused lambda, line 226)."""
+    model = SentimentModel(embedding_dim, hidden_dim, n_out)
+    model.load_state_dict(torch.load(path))
+    return model.to(device)
+
+
+def _index_batches(loader, device):
+    """The index batches ``for j, senti in loader`` would yield, with the same draws from the
+    global generator in the same order (num_workers = 0: the iterator's base seed first, then the
+    RandomSampler's seed when the first batch is requested)."""
+    torch.empty((), dtype=torch.int64).random_(generator=loader.generator)
+    for idx in loader.batch_sampler:
+        yield torch.as_tensor(idx, dtype=torch.int64).to(device, non_blocking=True)
+
+
+def _l1(model, latents, labels, j):
+    senti = labels[j]
+    return (model(latents[j]).reshape(senti.shape) - senti).abs(), senti
+
+
 def predict_sentiment(data, model, latents):
-    """reference sentiment_model.py:51-74 -- predictions and targets as NumPy arrays."""
+    """reference sentiment_model.py:51-74 -- predictions and targets as NumPy arrays (in the
+    loader's shuffled order, like the reference; the metrics do not depend on the order)."""
+    labels = data.dataset.sentiment
     ys, ps = [], []
+    total = torch.zeros((), device=labels.device)
     with torch.no_grad():
-        for j, senti in data:
+        for j in _index_batches(data, labels.device):
+            senti = labels[j]
+            p = model(latents[j]).reshape(senti.shape)
+            total += (p - senti).abs().sum()
             ys.append(senti)
-            ps.append(model(latents[j]).reshape(senti.shape))
-    y, p = torch.cat(ys), torch.cat(ps)
-    print("MAE: {}".format(float((p - y).abs().sum() / len(data.dataset))))
-    return p.cpu().numpy(), y.cpu().numpy()
+            ps.append(p)
+    print("MAE: {}".format(float(total) / len(data.dataset)))
+    return torch.cat(ps).cpu().numpy(), torch.cat(ys).cpu().numpy()
 
 
 class _GraphedSentimentStep(object):
@@ -65,8 +105,7 @@ class _GraphedSentimentStep(object):
         self.graphs = {}
 
     def _step(self, j):
-        senti = self.labels[j]
-        loss = (self.model(self.latents[j]).reshape(senti.shape) - senti).abs().mean()
+        loss = _l1(self.model, self.latents, self.labels, j)[0].mean()
         loss.backward()
         self.optimizer.step()
         return loss.detach()
@@ -99,80 +138,157 @@ class _GraphedSentimentStep(object):
         return static_loss
 
 
-def train_sentiment(args, model, train_data, train_latents, valid_data=None, valid_latents=None,
-                    model_save_path=None):
-    """reference sentiment_model.py:76-163 -- SGD on the L1 loss; with ``early_stopping`` the best
-    validation checkpoint is restored and the step size decayed by ``lr_decay`` on plateaus."""
+def train_sentiment(args, model, train_data, train_latents, valid_data, valid_latents, model_loader=None,
+                    valid_niter=10, verbose=False, model_save_path=None):
+    """reference sentiment_model.py:76-163 -- plain SGD on the mean L1 loss, batches of the shuffled
+    loader; every ``valid_niter`` epochs one pass over the validation loader.  With
+    ``args['early_stopping']``: patience 10 validations, then reload the best checkpoint (model +
+    optimizer, when a save path is given) and multiply the step size by ``args['lr_decay']``, at most
+    3 times.  Returns ``(train_losses, valid_losses)`` (per-epoch / per-validation batch means)."""
+    n_epochs = args['n_sentiment_epochs']
     lr = args['sentiment_lr']
+    patience, n_trials = 10, 3
+    n_samples = len(train_data.dataset)
+    device = train_latents.device
+    labels, valid_labels = train_data.dataset.sentiment, valid_data.dataset.sentiment
     optimizer = optim.SGD(model.parameters(), lr=lr)
-    best, best_state, patience, trials = float('inf'), None, 0, 0
-    train_losses, valid_losses = [], []
     graphed = str(args.get('cuda_graph', 0)) not in ('0', 'False', 'false', '') and train_latents.is_cuda
-    stepper = _GraphedSentimentStep(model, train_latents, train_data.dataset.sentiment, optimizer) if graphed else None
-    for _ in range(args['n_sentiment_epochs']):
-        if graphed:
-            # SURVEY.md 8f N4: each SGD step is one graph replay; the epoch loss is read back once
-            total_t = torch.zeros((), device=train_latents.device)
-            torch.empty((), dtype=torch.int64).random_(generator=train_data.generator)   # the DataLoader's base seed
-            for idx in train_data.batch_sampler:
-                total_t += stepper(torch.as_tensor(idx, dtype=torch.int64).to(train_latents.device, non_blocking=True))
-            total = float(total_t)
-        else:
-            total = 0.
-            for j, senti in train_data:
-                optimizer.zero_grad()
-                loss = (model(train_latents[j]).reshape(senti.shape) - senti).abs().mean()
+    stepper = _GraphedSentimentStep(model, train_latents, labels, optimizer) if graphed else None
+    ckpt_file = os.path.join(model_save_path, 'senti.bin') if model_save_path is not None else None
+
+    train_losses, valid_losses = [], []
+    n_bad = n_bad_trials = 0
+    i, epoch_loss = -1, torch.zeros((), device=device)
+    for i in range(n_epochs):
+        epoch_loss = torch.zeros((), device=device)
+        n_batches = 0
+        for j in _index_batches(train_data, device):
+            n_batches += 1
+            if graphed:
+                epoch_loss += stepper(j)
+            else:
+                model.zero_grad()
+                loss = _l1(model, train_latents, labels, j)[0].mean()
                 loss.backward()
                 optimizer.step()
-                total += float(loss)
-        train_losses.append(total)
-        if args.get('early_stopping') and valid_data is not None:
+                epoch_loss += loss.detach()
+        train_losses.append(float(epoch_loss) / max(n_batches, 1))
+        if i % valid_niter == 0:
+            batches = 0
+            valid_loss = torch.zeros((), device=device)
             with torch.no_grad():
-                v = sum(float((model(valid_latents[j]).reshape(s.shape) - s).abs().sum()) for j, s in valid_data)
-            valid_losses.append(v)
-            if v < best:
-                best, patience = v, 0
-                best_state = {k: t.clone() for k, t in model.state_dict().items()}
-            else:
-                patience += 1
-                if patience >= 5:
-                    trials, patience = trials + 1, 0
-                    if trials >= 5:
-                        print("early stopping...")
-                        break
-                    lr = lr * args.get('lr_decay', 0.5)
-                    model.load_state_dict(best_state)
-                    optimizer = optim.SGD(model.parameters(), lr=lr)
-                    if graphed:
-                        stepper = _GraphedSentimentStep(model, train_latents, train_data.dataset.sentiment, optimizer)
-    if best_state is not None:
-        model.load_state_dict(best_state)
+                for j in _index_batches(valid_data, device):
+                    valid_loss += _l1(model, valid_latents, valid_labels, j)[0].mean()
+                    batches += 1
+            avg_valid_loss = float(valid_loss) / max(batches, 1)
+            print("Epoch {}: {} (avg val loss {})".format(i, train_losses[-1], avg_valid_loss))
+            is_better = len(valid_losses) == 0 or avg_valid_loss < min(valid_losses)
+            valid_losses.append(avg_valid_loss)
+            if args['early_stopping']:
+                if is_better:
+                    n_bad = 0
+                    if ckpt_file is not None:
+                        torch.save({'model_state_dict': model.state_dict(),
+                                    'optimizer_state_dict': optimizer.state_dict()}, ckpt_file)
+                else:
+                    print('patience {}'.format(n_bad))
+                    n_bad += 1
+                    if n_bad >= patience:
+                        n_bad_trials += 1
+                        if n_bad_trials < n_trials:
+                            if ckpt_file is not None:
+                                print("reloading model and decaying learning rate...")
+                                checkpoint = torch.load(ckpt_file)
+                                model.load_state_dict(checkpoint['model_state_dict'])
+                                optimizer.load_state_dict(checkpoint['optimizer_state_dict'])
+                            lr = lr * args['lr_decay']
+                            for g in optimizer.param_groups:
+                                g['lr'] = lr
+                            if graphed:   # the step size is baked into the captured update
+                                stepper = _GraphedSentimentStep(model, train_latents, labels, optimizer)
+                            n_bad = 0
+                        else:
+                            print("early stopping...")
+                            break
+    print("Epoch {}: {}".format(i, float(epoch_loss) / max(n_samples, 1)))
     return train_losses, valid_losses
 
 
 def _score(args, predictions, y):
     if args['dataset'] == 'mosi':
         return full_loss(predictions, y)
-    if args['dataset'] == 'pom':
-        return pom_loss(predictions, y)
-    return iemocap_loss(predictions, y)
+    elif args['dataset'] == 'iemocap':
+        return iemocap_loss(predictions, y)
+    return pom_loss(predictions, y)
 
 
-def train_sentiment_for_latents(args, latents, sentiment_data, device, train_idxes=None, model_save_path=None):
-    """reference sentiment_model.py:165-265 -- fit the regressor on the train latents, report the
-    dataset's metrics on the test latents, write ``test_results_after.json``."""
+def train_sentiment_for_latents(args, latents, sentiment_data, device, verbose=False, model_save_path=None,
+                                train_idxes=None):
+    """reference sentiment_model.py:165-265 -- fit the regressor on the train latents, score the test
+    latents before and after with the dataset's metrics, write ``test_results_{before,after}.json``,
+    ``test_acc_*.txt``, ``senti_{train,valid}_loss.txt`` and ``senti.bin`` under ``model_save_path``.
+    Like the reference, the final scores come from the model as training left it (the reference
+    loads its best checkpoint into a second model that it never uses, lines 247-251).
+    The reference returns None; this returns ``(results_after, (train_losses, valid_losses))``."""
     train_latents, valid_latents, test_latents = latents
-    train_s, valid_s, test_s = sentiment_data
-    n_out = 1 if train_s.ndim == 1 else train_s.shape[-1]
+    hidden_dim = args['sentiment_hidden_size']
+    embedding_dim = train_latents.size()[-1]
+    train, valid, test = sentiment_data
+    n_out = 1 if train.ndim == 1 else train.shape[-1]
+    senti_model = SentimentModel(embedding_dim, hidden_dim, n_out).to(device)
+
+    print("train data shape:", train.shape)
+    print("train latents shape:", train_latents.size())
     if train_idxes is not None:
-        train_latents, train_s = train_latents[train_idxes], train_s[train_idxes]
-    loaders = [DataLoader(SentimentData(s, device), batch_size=32, shuffle=sh)
-               for s, sh in ((train_s, True), (valid_s, False), (test_s, False))]
-    model = SentimentModel(train_latents.shape[-1], args['sentiment_hidden_size'], n_out).to(device)
-    losses_ = train_sentiment(args, model, loaders[0], train_latents, loaders[1], valid_latents, model_save_path)
-    predictions, y = predict_sentiment(loaders[2], model, test_latents)
-    results = _score(args, predictions, y)
+        train = train[train_idxes]
+        train_latents = train_latents[train_idxes]
+        print("train data shape:", train.shape)
+        print("train latents shape:", train_latents.size())
+
+    train_data, valid_data, test_data = (SentimentData(s, device) for s in (train, valid, test))
+    assert train_latents.size()[0] == train.shape[0]
+    print("# of sentiment points:", len(train_data))
+    train_loader = DataLoader(train_data, batch_size=32, shuffle=True)
+    valid_loader = DataLoader(valid_data, batch_size=32, shuffle=True)
+    test_loader = DataLoader(test_data, batch_size=32, shuffle=True)
+
+    print("Initial sentiment predictions")
+    senti_model.eval()
+    predictions, y_test = predict_sentiment(test_loader, senti_model, test_latents)
+    results = _score(args, predictions, y_test)
     if model_save_path is not None:
+        if 'accuracy' in results:
+            with open(os.path.join(model_save_path, 'test_acc_before.txt'), 'w') as f:
+                f.write(str(results['accuracy']))
+        with open(os.path.join(model_save_path, 'test_results_before.json'), 'w') as f:
+            json.dump(results, f, indent=2)
+
+    print("Training sentiment model on sentence embeddings...")
+    senti_model.train()
+    train_losses, valid_losses = train_sentiment(args, senti_model, train_loader, train_latents, valid_loader,
+                                                 valid_latents, None, verbose=verbose,
+                                                 model_save_path=model_save_path)
+    if model_save_path is not None:
+        for name, vals in (('senti_train_loss.txt', train_losses), ('senti_valid_loss.txt', valid_losses)):
+            with open(os.path.join(model_save_path, name), 'w') as f:
+                f.writelines('{}\n'.format(v) for v in vals)
+        if not args['early_stopping']:
+            save_sentiment(model_save_path, senti_model)
+    if args['early_stopping']:
+        # the reference builds a second model here for the best checkpoint and then scores the first
+        # one (lines 247-251); only its draws from the global generator have any effect
+        print('reloading best')
+        SentimentModel(embedding_dim, hidden_dim, n_out)
+
+    print("Sentiment predictions after training")
+    senti_model.eval()
+    predictions, y_test = predict_sentiment(test_loader, senti_model, test_latents)
+    results = _score(args, predictions, y_test)
+    if model_save_path is not None:
+        if 'accuracy' in results:
+            with open(os.path.join(model_save_path, 'test_acc_after.txt'), 'w') as f:
+                f.write(str(results['accuracy']))
         with open(os.path.join(model_save_path, 'test_results_after.json'), 'w') as f:
             json.dump(results, f, indent=2)
-    return results, losses_
+    print("-----------------------------")
+    return results, (train_losses, valid_losses)

@@ -321,10 +321,15 @@ def make_word_log_prob_fn(args, weights, word_embeddings, a=1e-3):
 
 
 def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, senti_train_data, senti_mask,
-                     word_prob_fn, device, n_epochs=None, verbose=True):
-    """The e2e loop of reference simplesif.py:694-790: latents, generator heads and the
+                     word_prob_fn, device, n_epochs=None, verbose=True, validation_data=None):
+    """The e2e loop of reference simplesif.py:694-800: latents, generator heads and the
     sentiment regressor are optimised jointly on
-    ``likelihood_weight * (-log p) + (1 - likelihood_weight) * L1(sentiment) * senti_mask``."""
+    ``likelihood_weight * (-log p) + (1 - likelihood_weight) * L1(sentiment) * senti_mask``.
+    ``validation_data = (valid_embedding, valid_dataloader)``: every 80 epochs the validation latents
+    are optimised for ``n_epochs`` with the current heads and their last epoch loss recorded
+    (reference 796-800) -- besides the number it reports, that pass draws from torch's global
+    generator (one DataLoader base seed per epoch), so it is part of reproducing the reference's
+    batch order.  Returns ``(train_embed, (train_losses, all_valid_losses))``."""
     train_embed = torch.tensor(np.array(train_embedding, copy=True), device=device, dtype=torch.float32)
     train_embed.requires_grad = True
     grad_params = [train_embed] + list(gen_model.parameters()) + list(senti_model.parameters())
@@ -347,9 +352,10 @@ def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, 
 
     stepper = GraphedStep(args, gen_model, train_embed, dataloader.dataset, optimizer, word_prob_fn, device,
                           extra_loss=mixed_loss, extra_modules=[senti_model]) if graphed else None
-    train_losses = []
+    train_losses, all_valid_losses = [], []
     start_time = time.time()
-    for i in range(n_epochs if n_epochs is not None else args['n_epochs']):
+    n_epochs = n_epochs if n_epochs is not None else args['n_epochs']
+    for i in range(n_epochs):
         epoch_loss = torch.zeros((), device=device)
         iters = 0
         if graphed:
@@ -370,10 +376,18 @@ def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, 
                 optimizer.step()
                 epoch_loss += loss.detach()
         train_losses.append(float(epoch_loss))
-        if verbose and i % 10 == 0:
-            print("epoch {}: {} ({}s)".format(i, train_losses[-1] / max(iters, 1), time.time() - start_time))
+        if i % 10 == 0:
+            if verbose:
+                print("epoch {}: {} ({}s)".format(i, train_losses[-1] / max(iters, 1), time.time() - start_time))
+            if validation_data is not None and i % 80 == 0:
+                valid_embedding, valid_dataloader = validation_data
+                _, (valid_losses, _) = optimize_latents(args, False, gen_model, valid_embedding, valid_dataloader,
+                                                        n_epochs, args['lr'], word_prob_fn, device, verbose=False)
+                if verbose:
+                    print("Validation loss:", valid_losses[-1])
+                all_valid_losses.append(valid_losses[-1])
     train_embed.requires_grad = False
-    return train_embed, train_losses
+    return train_embed, (train_losses, all_valid_losses)
 
 
 def read_config(config_file):
@@ -453,6 +467,69 @@ def prepare_splits(args, word_embeddings, weights, splits, masks, device):
     return embeddings, w_t, we_t
 
 
+def run_experiment(args, word_embeddings, weights, splits, masks, device, folder=None):
+    """Everything reference simplesif.py:294-914 does once the splits are loaded and normalised
+    (``masks`` already hold the text mask of ``update_masks``): SIF initialisation per split, id
+    expansion and positional columns, datasets / loaders, then per run the e2e branch (625-806) or
+    the two-stage branch (541-624), latent inference for valid / test and the downstream regressor.
+    ``folder`` (a format string taking the run number, or None) is where the reference's artefacts
+    go.  Returns the list of per-run ``(results, train_losses, (train, valid, test) latents)``."""
+    embeddings, w_t, we_t = prepare_splits(args, word_embeddings, weights, splits, masks, device)
+    train, valid, test = splits
+
+    def dataset(s, m):
+        if args['dataset'] == 'mosi':
+            return MMData(s['text'], s['covarep'], s['facet'], m, s['text_weights'], device)
+        return MMDataExtra(s['text'], s['covarep'], s['facet'], m, s['text_weights'], s['text_align'], device)
+    bs = args['batch_size']
+    loaders = [DataLoader(dataset(train, masks[0]), batch_size=bs, shuffle=True),
+               DataLoader(dataset(valid, masks[1]), batch_size=bs * 8),
+               DataLoader(dataset(test, masks[2]), batch_size=bs * 8)]
+    word_fn = make_word_log_prob_fn(args, w_t, we_t)
+    d, A, Vd = train['text'].shape[-1], train['covarep'].shape[-1], train['facet'].shape[-1]
+    sentiment_data = (train['label'], valid['label'], test['label'])
+
+    runs = []
+    for r in range(args['n_runs']):
+        run_dir = folder.format(r) if folder is not None else None
+        if run_dir is not None:
+            for sub in ('pre', 'post'):
+                os.makedirs(os.path.join(run_dir, sub), exist_ok=True)
+            json.dump(args, open(os.path.join(run_dir, 'config.json'), 'w'), indent=2)
+            torch.save(torch.tensor(np.concatenate(embeddings, axis=0), device=device, dtype=torch.float32),
+                       os.path.join(run_dir, 'pre', 'embed.bin'))
+        gen_model = AudioVisualGeneratorMultimodal(d, A, Vd, norm=args['norm'], frozen_weights=args['freeze_weights'],
+                                                   unimodal=args['unimodal']).to(device)
+        n_epochs, lr = args['n_epochs'], args['lr']
+        if args['e2e']:
+            n_out = 1 if train['label'].ndim == 1 else train['label'].shape[-1]
+            senti_model = SentimentModel(d, args['sentiment_hidden_size'], n_out).to(device)
+            senti_mask = torch.ones(len(train['label']), device=device)
+            train_embed, (train_losses, valid_losses) = train_end_to_end(
+                args, gen_model, senti_model, embeddings[0], loaders[0], SentimentData(train['label'], device),
+                senti_mask, word_fn, device, validation_data=(embeddings[1], loaders[1]))
+        else:
+            train_embed, (train_losses, valid_losses) = optimize_latents(
+                args, True, gen_model, embeddings[0], loaders[0], n_epochs, lr, word_fn, device,
+                validation_data=(embeddings[1], loaders[1]))
+        valid_embed, _ = optimize_latents(args, False, gen_model, embeddings[1], loaders[1], n_epochs, lr,
+                                          word_fn, device)
+        test_embed, (test_losses, _) = optimize_latents(args, False, gen_model, embeddings[2], loaders[2], n_epochs,
+                                                        lr, word_fn, device)
+        post = None
+        if run_dir is not None:
+            for name, vals in (('embed_loss.txt', train_losses), ('embed_valid_loss.txt', valid_losses),
+                               ('embed_test_loss.txt', test_losses)):
+                with open(os.path.join(run_dir, name), 'w') as f:
+                    f.writelines('{}\n'.format(v) for v in vals)
+            post = os.path.join(run_dir, 'post')
+            torch.save(torch.cat([train_embed, valid_embed, test_embed], dim=0), os.path.join(post, 'embed.bin'))
+        results, _ = train_sentiment_for_latents(args, (train_embed, valid_embed, test_embed), sentiment_data, device,
+                                                 model_save_path=post)
+        runs.append((results, train_losses, (train_embed, valid_embed, test_embed)))
+    return runs
+
+
 def main(argv=None):
     """reference simplesif.py:240-916, for the datasets the reference's loaders can open."""
     args = parse_arguments(argv)
@@ -472,55 +549,9 @@ def main(argv=None):
     weights = load_weights(args)
     if args['word_sim_metric'] == 'dot_prod':
         word_embeddings = word_embeddings / np.linalg.norm(word_embeddings, axis=-1, keepdims=True)
-    embeddings, w_t, we_t = prepare_splits(args, word_embeddings, weights, splits, masks, device)
-    train, valid, test = splits
-
-    def dataset(s, m):
-        if args['dataset'] == 'mosi':
-            return MMData(s['text'], s['covarep'], s['facet'], m, s['text_weights'], device)
-        return MMDataExtra(s['text'], s['covarep'], s['facet'], m, s['text_weights'], s['text_align'], device)
-    bs = args['batch_size']
-    loaders = [DataLoader(dataset(train, masks[0]), batch_size=bs, shuffle=True),
-               DataLoader(dataset(valid, masks[1]), batch_size=bs * 8),
-               DataLoader(dataset(test, masks[2]), batch_size=bs * 8)]
-    word_fn = make_word_log_prob_fn(args, w_t, we_t)
-    d, A, Vd = train['text'].shape[-1], train['covarep'].shape[-1], train['facet'].shape[-1]
-    sentiment_data = (train['label'], valid['label'], test['label'])
-
-    for r in range(args['n_runs']):
-        config_name = args['config_name'] or os.path.split(os.path.split(args['config_file'])[0])[1]
-        folder = 'model_saves/{}/config_{}_run_{}'.format(config_name, args['config_num'], r)
-        for sub in ('pre', 'post'):
-            os.makedirs(os.path.join(folder, sub), exist_ok=True)
-        json.dump(args, open(os.path.join(folder, 'config.json'), 'w'), indent=2)
-        torch.save(torch.tensor(np.concatenate(embeddings, axis=0), device=device, dtype=torch.float32),
-                   os.path.join(folder, 'pre', 'embed.bin'))
-        gen_model = AudioVisualGeneratorMultimodal(d, A, Vd, norm=args['norm'], frozen_weights=args['freeze_weights'],
-                                                   unimodal=args['unimodal']).to(device)
-        n_epochs, lr = args['n_epochs'], args['lr']
-        if args['e2e']:
-            n_out = 1 if train['label'].ndim == 1 else train['label'].shape[-1]
-            senti_model = SentimentModel(d, args['sentiment_hidden_size'], n_out).to(device)
-            senti_mask = torch.ones(len(train['label']), device=device)
-            train_embed, train_losses = train_end_to_end(args, gen_model, senti_model, embeddings[0], loaders[0],
-                                                         SentimentData(train['label'], device), senti_mask,
-                                                         word_fn, device)
-            valid_losses = []
-        else:
-            train_embed, (train_losses, valid_losses) = optimize_latents(
-                args, True, gen_model, embeddings[0], loaders[0], n_epochs, lr, word_fn, device,
-                validation_data=(embeddings[1], loaders[1]))
-        valid_embed, _ = optimize_latents(args, False, gen_model, embeddings[1], loaders[1], n_epochs, lr,
-                                          word_fn, device)
-        test_embed, (test_losses, _) = optimize_latents(args, False, gen_model, embeddings[2], loaders[2], n_epochs,
-                                                        lr, word_fn, device)
-        for name, vals in (('embed_loss.txt', train_losses), ('embed_valid_loss.txt', valid_losses),
-                           ('embed_test_loss.txt', test_losses)):
-            with open(os.path.join(folder, name), 'w') as f:
-                f.writelines('{}\n'.format(v) for v in vals)
-        torch.save(torch.cat([train_embed, valid_embed, test_embed], dim=0), os.path.join(folder, 'post', 'embed.bin'))
-        train_sentiment_for_latents(args, (train_embed, valid_embed, test_embed), sentiment_data, device,
-                                    model_save_path=os.path.join(folder, 'post'))
+    config_name = args['config_name'] or os.path.split(os.path.split(args['config_file'])[0])[1]
+    folder = 'model_saves/{}/config_{}_run_{{}}'.format(config_name, args['config_num'])
+    run_experiment(args, word_embeddings, weights, splits, masks, device, folder=folder)
 
 
 if __name__ == '__main__':

@@ -157,9 +157,9 @@ def run_config(cfg, prep, epochs_scale=1.0, cuda_graph=True, verbose=False):
     if not verbose:
         sys.stdout = buf
     try:
-        train_embed, train_losses = simplesif.train_end_to_end(
+        train_embed, (train_losses, _) = simplesif.train_end_to_end(
             args, gen_model, senti_model, prep.embeddings[0], loaders[0], SentimentData(prep.labels[0], device),
-            senti_mask, word_fn, device, verbose=False)
+            senti_mask, word_fn, device, verbose=False, validation_data=(prep.embeddings[1], loaders[1]))
         valid_embed, _ = simplesif.optimize_latents(args, False, gen_model, prep.embeddings[1], loaders[1],
                                                     args['n_epochs'], args['lr'], word_fn, device, verbose=False)
         test_embed, (test_losses, _) = simplesif.optimize_latents(args, False, gen_model, prep.embeddings[2],

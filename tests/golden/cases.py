@@ -190,3 +190,91 @@ def closed_form_data(c):
     return {'audio': c['aud'], 'visual': c['vis'], 'audiovisual': cat(c['aud'], c['vis']),
             'textaudio': cat(c['text'], c['aud']), 'textvisual': cat(c['text'], c['vis']),
             'textaudiovisual': cat(c['text'], c['aud'], c['vis'])}
+
+
+# Downstream parity (north_star: "MOSI/POM MAE and correlation unchanged to the 3rd decimal"): the
+# whole script path -- SIF initialisation per split, latent optimisation, regressor -- on small
+# labelled synthetic splits, run through the reference (make_golden.golden_downstream) and through
+# this repo (tests/test_mmb_gpu.py) from the same seed.
+_DS_ARGS = {'unimodal': False, 'freeze_weights': False, 'word_sim_metric': 'angular', 'batch_size': 64,
+            'n_runs': 1, 'semi_sup_idxes': None, 'config_name': 'golden', 'config_num': 0, 'lr_decay': 0.5,
+            'early_stopping': False, 'time_test': False, 'seq_len': 20, 'sentiment_hidden_size': 100,
+            'word_loss_weight': 0.002, 'likelihood_weight': 0.001, 'pos_embed_dim': 2}
+DOWNSTREAM_CASES = {
+    # the e2e branch (reference simplesif.py:625-806; every generated config has e2e=True)
+    'mosi_e2e': dict(n=(160, 48, 80), L=12, T_a=None, V=400, d=300, A=10, Vd=8, n_out=1, seed=71,
+                     args=dict(_DS_ARGS, dataset='mosi', e2e=True, optimizer='sgd', norm='layer_norm', lr=1e-3,
+                               sentiment_lr=0.1, n_epochs=12, n_sentiment_epochs=41)),
+    # the two-stage branch (simplesif.py:541-624) on the POM layout: unaligned ids for the word term,
+    # aligned word vectors for the Gaussian terms (MMDataExtra), several traits -> pom_loss
+    'pom_two_stage': dict(n=(130, 40, 70), L=16, T_a=24, V=300, d=300, A=9, Vd=7, n_out=3, seed=72,
+                          args=dict(_DS_ARGS, dataset='pom', e2e=False, optimizer='adam', norm=None, lr=1e-3,
+                                    sentiment_lr=0.1, n_epochs=11, n_sentiment_epochs=31)),
+}
+
+
+def downstream_inputs(n, L, T_a, V, d, A, Vd, n_out, seed, args):
+    """Three labelled splits in the layout the reference's loaders + normalize_data hand to main():
+    ids (N, L) right-padded with 0, covarep / facet in [-1, 1] with padded steps -10 and int masks
+    (utils.py:171-189), labels that depend on the words (and the first audio feature on the labels)."""
+    rng = np.random.default_rng(seed)
+    We = table(V, d, seed + 100)
+    U = rng.standard_normal((d, n_out))
+    splits, masks, weights = [], [], None
+    for k, nk in enumerate(n):
+        ids, p = zipf_ids(rng, nk, L, V, lo_len=3)
+        if weights is None:
+            weights = sif_weights(p)
+        lens = (ids != 0).sum(1)
+        T = L if T_a is None else T_a
+        if T_a is None:
+            step_len = lens
+        else:   # aligned stream: every word held for 1..2 frames, cut to T_a
+            rep = rng.integers(1, 3, size=ids.shape)
+            ids_a = np.zeros((nk, T_a), dtype=np.int64)
+            for i in range(nk):
+                row = np.repeat(ids[i], rep[i])
+                row = row[row != 0][:T_a]
+                ids_a[i, :row.size] = row
+            step_len = (ids_a != 0).sum(1)
+        step = np.arange(T)[None, :, None] < step_len[:, None, None]
+        avg = (We[ids] * weights[ids][:, :, None]).sum(1) / L           # labels: a noisy function of the
+        z = (avg - avg.mean(0)) @ U                                       # (centred) weighted average
+        y = 3.0 * np.tanh(0.7 * z / z.std(0)) + 0.3 * rng.standard_normal((nk, n_out))
+        cov = rng.uniform(-1, 1, (nk, T, A))
+        fac = rng.uniform(-1, 1, (nk, T, Vd))
+        cov[:, :, 0] = np.clip(cov[:, :, 0] * 0.5 + y[:, :1] / 6.0, -1, 1)
+        cov_m = np.broadcast_to(step, cov.shape).astype(np.int64).copy()
+        fac_m = np.broadcast_to(step, fac.shape).astype(np.int64).copy()
+        cov[cov_m == 0] = -10.0
+        fac[fac_m == 0] = -10.0
+        s = {'covarep': cov, 'facet': fac, 'label': (y[:, 0] if n_out == 1 else y).astype(np.float32)}
+        if T_a is None:
+            s['text'] = ids
+        else:
+            s['text_id'] = ids
+            s['text'] = We[ids_a].astype(np.float32)          # aligned word vectors (zero rows = padding)
+        splits.append(s)
+        masks.append({'covarep': cov_m, 'facet': fac_m})
+    return We, weights, splits, masks
+
+
+# sentiment_model.train_sentiment_for_latents alone (pure torch, runs on the CPU on both sides): fixed
+# random latents, labels a noisy function of them.
+SENTIMENT_CASES = {
+    'mosi': dict(dataset='mosi', n_out=1, early_stopping=False, seed=81),
+    'pom': dict(dataset='pom', n_out=3, early_stopping=False, seed=82),
+    'mosi_early_stopping': dict(dataset='mosi', n_out=1, early_stopping=True, seed=83),
+}
+
+
+def sentiment_inputs(dataset, n_out, early_stopping, seed, d=30, sizes=(150, 45, 70)):
+    rng = np.random.default_rng(seed)
+    lat = [rng.standard_normal((n, d)).astype(np.float32) for n in sizes]
+    U = rng.standard_normal((d, n_out))
+    labs = [(np.tanh(x @ U) * 3 + 0.3 * rng.standard_normal((len(x), n_out))).astype(np.float32) for x in lat]
+    if n_out == 1:
+        labs = [y[:, 0] for y in labs]
+    args = {'dataset': dataset, 'sentiment_hidden_size': 20, 'n_sentiment_epochs': 95, 'sentiment_lr': 0.1,
+            'early_stopping': early_stopping, 'lr_decay': 0.5}
+    return args, lat, labs

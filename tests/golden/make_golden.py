@@ -214,6 +214,145 @@ def golden_utils():
          m_facet=masks['facet'])
 
 
+def golden_downstream():
+    """The script path end to end through the UNMODIFIED reference on small labelled splits:
+    sif.get_sentence_embeddings per split -> id expansion / positional columns (simplesif.py:296-399,
+    restated from main(), which cannot be imported) -> MMData / DataLoader (442-459) -> the e2e block
+    (simplesif.py:671-806, executed from the source file) or the two-stage branch (optimize_latents,
+    588-610) -> sentiment_model.train_sentiment_for_latents -> test_results_{before,after}.json."""
+    import json
+    import tempfile
+    import textwrap
+    import time
+    import torch.nn as nn
+    import torch.optim as optim
+    from torch.utils.data import DataLoader
+    import utils_stub
+    import sentiment_model as ref_sm
+    assert ref_sm.__file__.startswith(REF)
+    src = open(os.path.join(REF, 'simplesif.py')).read().split('\n')
+    ns = {'torch': torch, 'optim': optim, 'time': time, 'np': np, 'nn': nn,
+          'get_log_prob_matrix': ref_losses.get_log_prob_matrix}
+    exec(compile('\n'.join(src[35:47]), 'reference simplesif.py:36-47', 'exec'), ns)
+    exec(compile('\n'.join(src[48:162]), 'reference simplesif.py:49-162', 'exec'), ns)
+    e2e_block = textwrap.dedent('\n'.join(src[670:806]))
+    out = {}
+    device = torch.device('cpu')
+    for tag, cfg in cases.DOWNSTREAM_CASES.items():
+        args = dict(cfg['args'])
+        We, weights, splits, masks = cases.downstream_inputs(**cfg)
+        torch.manual_seed(cfg['seed'])
+        id_key = 'text' if args['dataset'] == 'mosi' else 'text_id'
+        for s, m in zip(splits, masks):
+            ns['update_masks'](m, s[id_key], We.shape[-1])
+        emb = [ref_sif.get_sentence_embeddings(We, weights, s[id_key]) for s in splits]
+        w_t = torch.tensor(weights, device=device, dtype=torch.float32)
+        we_t = torch.tensor(We, device=device, dtype=torch.float32)
+        for s, m in zip(splits, masks):                       # simplesif.py:319-399
+            if args['dataset'] == 'mosi':
+                s['text_id'] = s['text']
+            else:
+                s['text_align'] = s['text']
+                ns['update_masks_vect'](m, s['text_align'], 'text_align')
+            s['text'] = we_t[s['text_id']]
+            s['text_weights'] = w_t[s['text_id']]
+            n_points, seq_len = m['covarep'].shape[:2]
+            ext = np.ones((n_points, seq_len, args['pos_embed_dim']), dtype=np.int64)
+            for k in ('covarep', 'facet'):
+                s[k] = utils_stub.add_positional_embeddings(args, s[k])
+                m[k] = np.concatenate([m[k], ext], axis=-1)
+        train, valid, test = splits
+
+        def dataset(s, m):
+            if args['dataset'] == 'mosi':
+                return utils_stub.MMData(s['text'], s['covarep'], s['facet'], m, s['text_weights'], device)
+            return utils_stub.MMDataExtra(s['text'], s['covarep'], s['facet'], m, s['text_weights'],
+                                          s['text_align'], device)
+        bs = args['batch_size']
+        dataloader = DataLoader(dataset(train, masks[0]), batch_size=bs, shuffle=True)
+        valid_dataloader = DataLoader(dataset(valid, masks[1]), batch_size=bs * 8)
+        test_dataloader = DataLoader(dataset(test, masks[2]), batch_size=bs * 8)
+
+        def get_word_log_prob2(latents, word_weights, sent_embeddings, mask):   # simplesif.py:527-537
+            return ref_losses.get_word_log_prob_angular2(latents, we_t, word_weights, sent_embeddings, mask, 1e-3)
+        sentiment_data = (train['label'], valid['label'], test['label'])
+        d, A, Vd = train['text'].shape[-1], train['covarep'].shape[-1], train['facet'].shape[-1]
+        if args['e2e']:
+            env = dict(ns)
+            env.update(AudioVisualGeneratorMultimodal=ref_models.AudioVisualGeneratorMultimodal, EMBEDDING_DIM=d,
+                       AUDIO_DIM=A, VISUAL_DIM=Vd, args=args, device=device, train=train,
+                       SentimentModel=ref_sm.SentimentModel, train_embedding=emb[0], valid_embedding=emb[1],
+                       test_embedding=emb[2], dataloader=dataloader, valid_dataloader=valid_dataloader,
+                       test_dataloader=test_dataloader, senti_train_data=ref_sm.SentimentData(train['label'], device),
+                       get_word_log_prob2=get_word_log_prob2, sentiment_train_idxes=None,
+                       senti_mask=torch.zeros(len(train['label']), device=device))
+            exec(compile(e2e_block, 'reference simplesif.py:671-806', 'exec'), env)
+            train_embed, valid_embed, test_embed = env['train_embed'], env['valid_embed'], env['test_embed']
+            train_losses = env['train_losses']
+        else:
+            gen_model = ref_models.AudioVisualGeneratorMultimodal(d, A, Vd, norm=args['norm'],
+                                                                  frozen_weights=args['freeze_weights'],
+                                                                  unimodal=args['unimodal']).to(device)
+            opt = ns['optimize_latents']
+            train_embed, (train_losses, _) = opt(args, True, gen_model, emb[0], dataloader, args['n_epochs'],
+                                                 args['lr'], get_word_log_prob2, device,
+                                                 validation_data=(emb[1], valid_dataloader))
+            valid_embed, _ = opt(args, False, gen_model, emb[1], valid_dataloader, args['n_epochs'], args['lr'],
+                                 get_word_log_prob2, device)
+            test_embed, _ = opt(args, False, gen_model, emb[2], test_dataloader, args['n_epochs'], args['lr'],
+                                get_word_log_prob2, device)
+        with tempfile.TemporaryDirectory() as tmp:
+            ref_sm.train_sentiment_for_latents(args, (train_embed.detach(), valid_embed, test_embed), sentiment_data,
+                                               device, train_idxes=None, model_save_path=tmp)
+            before = json.load(open(os.path.join(tmp, 'test_results_before.json')))
+            after = json.load(open(os.path.join(tmp, 'test_results_after.json')))
+        for nm, r in (('before', before), ('after', after)):
+            for k in ('mae', 'corr', 'mult_acc', 'f_score', 'accuracy'):
+                if k in r:
+                    out['%s_%s_%s' % (tag, nm, k)] = np.asarray(r[k], dtype=np.float64)
+        out[tag + '_sif_test'] = emb[2][:8]
+        out[tag + '_train_embed'] = train_embed.detach().numpy()[:8]
+        out[tag + '_test_embed'] = test_embed.detach().numpy()[:8]
+        out[tag + '_train_embed_sum'] = cases.checksum(train_embed.detach().numpy())
+        out[tag + '_test_embed_sum'] = cases.checksum(test_embed.detach().numpy())
+        out[tag + '_train_losses'] = np.asarray(train_losses, dtype=np.float64)
+        out[tag + '_inputs_sum'] = cases.checksum(np.concatenate([We.ravel()] + [s['covarep'].ravel() for s in splits]))
+    save('downstream.npz', **out)
+
+
+def golden_sentiment():
+    """reference sentiment_model.train_sentiment_for_latents on fixed latents (CPU)."""
+    import json
+    import tempfile
+    import sentiment_model as ref_sm
+    assert ref_sm.__file__.startswith(REF)
+    out = {}
+    for tag, cfg in cases.SENTIMENT_CASES.items():
+        args, lat, labs = cases.sentiment_inputs(**cfg)
+        torch.manual_seed(cfg['seed'])
+        with tempfile.TemporaryDirectory() as tmp:
+            ref_sm.train_sentiment_for_latents(args, tuple(torch.tensor(x) for x in lat), tuple(labs),
+                                               torch.device('cpu'), model_save_path=tmp)
+            for nm in ('before', 'after'):
+                r = json.load(open(os.path.join(tmp, 'test_results_%s.json' % nm)))
+                for k in ('mae', 'corr', 'mult_acc', 'f_score', 'accuracy'):
+                    if k in r:
+                        out['%s_%s_%s' % (tag, nm, k)] = np.asarray(r[k], dtype=np.float64)
+            out[tag + '_valid_losses'] = np.array([float(x) for x in open(os.path.join(tmp, 'senti_valid_loss.txt'))])
+        out[tag + '_next_draw'] = torch.rand(1).numpy()      # the global generator ends in the same state
+    save('sentiment.npz', **out)
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'sentiment':
+    golden_sentiment()
+    sys.exit(0)
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'downstream':
+    golden_downstream()
+    sys.exit(0)
+
+
 if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'closed_form':
     golden_closed_form()
     sys.exit(0)
@@ -223,3 +362,5 @@ if __name__ == '__main__':
     golden_optimize_latents()
     golden_utils()
     golden_closed_form()
+    golden_downstream()
+    golden_sentiment()

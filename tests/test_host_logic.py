@@ -114,3 +114,30 @@ def test_sweep_grid_matches_reference_generator():
     assert We.shape == (3016, 300) and weights.shape == (3016,) and weights[0] == 1.0
     assert [s['text'].shape for s in splits] == [(30, 20), (10, 20), (12, 20)]
     assert all((s['covarep'][s['text'] == 0] == 0).all() for s in splits)
+
+
+@pytest.mark.parametrize('tag', sorted(cases.SENTIMENT_CASES))
+def test_sentiment_regressor_matches_reference(golden_dir, tag, tmp_path, capsys):
+    """The downstream regressor is plain torch and 'unchanged' by the task's scope: on the CPU it must
+    reproduce the reference's sentiment_model.train_sentiment_for_latents -- metrics, validation curve,
+    files, and the state it leaves torch's global generator in (shuffles of later runs depend on it)."""
+    import torch
+    import sentiment_model
+    g = np.load(os.path.join(golden_dir, 'sentiment.npz'))
+    cfg = cases.SENTIMENT_CASES[tag]
+    args, lat, labs = cases.sentiment_inputs(**cfg)
+    torch.manual_seed(cfg['seed'])
+    results, (_, valid_losses) = sentiment_model.train_sentiment_for_latents(
+        args, tuple(torch.tensor(x) for x in lat), tuple(labs), torch.device('cpu'), model_save_path=str(tmp_path))
+    next_draw = torch.rand(1).numpy()
+    capsys.readouterr()
+    for k in ('mae', 'corr', 'mult_acc', 'f_score', 'accuracy'):
+        if k in results:
+            np.testing.assert_allclose(np.asarray(results[k], dtype=np.float64), g['%s_after_%s' % (tag, k)],
+                                       rtol=0, atol=2e-6, err_msg=k)
+    np.testing.assert_allclose(valid_losses, g[tag + '_valid_losses'], rtol=1e-6)
+    np.testing.assert_array_equal(next_draw, g[tag + '_next_draw'])
+    before = json.load(open(tmp_path / 'test_results_before.json'))
+    np.testing.assert_allclose(np.asarray(before['mae'], dtype=np.float64), g[tag + '_before_mae'], atol=2e-6)
+    for name in ('test_results_after.json', 'senti_train_loss.txt', 'senti_valid_loss.txt', 'senti.bin'):
+        assert (tmp_path / name).exists(), name
