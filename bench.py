@@ -73,10 +73,15 @@ def make_table_and_weights(device, V=VOCAB, d=DIM, seed=0):
     return table.contiguous(), torch.as_tensor(w.astype(np.float32)).to(device), p
 
 
+IDS_KIND = os.environ.get('MMB_BENCH_IDS', 'zipf')     # 'uniform': cache-hostile ids (secondary measurement)
+
+
 def make_ids(device, n_rows, L, p, seed, out=None, block=1 << 20):
     """Zipf ids over 1..V-1 by inverse-CDF on the device, right-padded with 0."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
+    if IDS_KIND == 'uniform':
+        p = np.full(p.size, 1.0 / p.size)
     cdf = torch.as_tensor(np.cumsum(p)).to(device=device, dtype=torch.float32)
     ids = out if out is not None else torch.empty((n_rows, L), dtype=torch.int64, device=device)
     ar = torch.arange(L, device=device)[None, :]
@@ -209,6 +214,33 @@ def load_tensor_peak():
             return float(json.load(fh)['bf16_tflops'])
     except Exception:
         return 1590.0
+
+
+def measure_tf32_peak(dev, n=8192, reps=10):
+    """Dense TF32 GEMM rate of this GPU, measured the way MEASURED_PEAKS.json measures bf16
+    (torch.matmul n^3, 2 n^3 FLOP, best of `reps`, CUDA events): the driver records no TF32 figure,
+    and the Gram kernel's pipe is kind::tf32.  Runs after the timed regions."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn((n, n), device=dev)
+        b = torch.randn((n, n), device=dev)
+        for _ in range(3):
+            torch.matmul(a, b)
+        best = None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def load_traffic(n_local):
@@ -366,10 +398,19 @@ def main():
 
     # ---- roofline of the dominant kernel + CPU baseline (rank 0) ---------------------------
     peak, peak_src = load_peaks()
+    tf32_peak = measure_tf32_peak(dev) if rank == 0 else None
+    tf32_src = 'measured here: torch.matmul TF32 8192^3, best of 10'
+    if not tf32_peak:
+        tf32_peak, tf32_src = load_tensor_peak() / 2.0, 'bf16_tflops / 2 (TF32, assumed)'
     embed_s = stage_ms['embed'] * 1e-3
+    traffic = load_traffic(n_local) if IDS_KIND == 'zipf' else None
     achieved = n_local * EMBED_BYTES_PER_UTT / embed_s / 1e9
     roofline = {'bound': 'hbm', 'kernel': 'sif_embed_warp_kernel<3,false>', 'achieved': achieved, 'peak': peak,
-                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': load_traffic(n_local),
+                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                # what HBM itself carried (ncu DRAM bytes of the committed capture / this run's launch time):
+                # the gap to `achieved` is rows served by L1/L2 (Zipf head + merged pad runs)
+                'dram_gbs': (traffic / embed_s / 1e9) if traffic else None,
+                'dram_frac': (traffic / embed_s / 1e9 / peak) if traffic else None,
                 'peak_source': peak_src, 'algorithmic_bytes_per_launch': n_local * EMBED_BYTES_PER_UTT,
                 'launch_ms': stage_ms['embed'], 'stage_ms': stage_ms,
                 # the other two streaming stages against their own bounds: the Gram's
@@ -379,8 +420,7 @@ def main():
                 'other_stages': {
                     'gram': {'bound': 'tensor', 'unit': 'TFLOP/s',
                              'achieved': n_local * 2.0 * DIM * DIM / (stage_ms['gram'] * 1e-3) / 1e12,
-                             'peak': load_tensor_peak() / 2.0, 'peak_source': 'bf16_tflops / 2 (TF32, assumed)',
-                             'executed_over_algorithmic': 2.05},
+                             'peak': tf32_peak, 'peak_source': tf32_src, 'executed_over_algorithmic': 2.05},
                     'project': {'bound': 'hbm', 'unit': 'GB/s',
                                 'achieved': n_local * 2.0 * DIM * 4 / (stage_ms['project'] * 1e-3) / 1e9,
                                 'peak': peak}}}
@@ -402,7 +442,8 @@ def main():
             'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'utterances': N_UTT, 'tokens_per_utterance': L_TOK, 'vocab': VOCAB,
-                       'dim': DIM, 'ids': 'Zipf(1.1), lengths U[16,64], pad id 0', 'npc': 1,
+                       'dim': DIM, 'ids': ('uniform over the vocabulary (cache-hostile variant)' if IDS_KIND == 'uniform'
+                                           else 'Zipf(1.1)') + ', lengths U[16,64], pad id 0', 'npc': 1,
                        'parallelism': 'utterance shards x%d + 1 all-reduce of the 300x300 Gram (%s)' % (
                            world, 'NVLink peer memory, fused into the Gram reduce kernel' if (world > 1 and mdist.default_comm() is not None) else 'NCCL' if world > 1 else 'none at 1 GPU'),
                        'l2': 'inputs larger than L2 (ids %.1f GB + embeddings %.1f GB per rank, table 0.48 GB)'
