@@ -348,6 +348,30 @@ if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'sentiment':
     sys.exit(0)
 
 
+def golden_pom_full():
+    """BASELINE config 3 at full size on the real fixtures: both POM splits in the tree (valid 100 x 1089,
+    test 203 x 1357, ids right-padded with 0 whose weight is 1.0) and the real pom_word_weights through
+    the reference's sif.get_sentence_embeddings; only the 300-d table is synthetic."""
+    pom_w = np.load(os.path.join(REF, 'pom', 'pom_word_weights.npy')).squeeze()
+    We = cases.table(7763, 300, seed=11)
+    out = dict(weights=pom_w, table_sum=cases.checksum(We))
+    for split in ('valid', 'test'):
+        ids = np.load(os.path.join(REF, 'pom', 'pom_%s_ids.npy' % split))
+        assert ids.max() < 2 ** 15 and ids.min() >= 0
+        w = ref_sf.seq2weight(ids, np.ones(ids.shape), pom_w)
+        avg = ref_sf.get_weighted_average(We, ids, w)
+        emb = ref_sif.get_sentence_embeddings(We, pom_w, ids)
+        out.update({split + '_ids': ids.astype(np.int16), split + '_w_nonzero': np.count_nonzero(w, axis=1),
+                    split + '_avg': avg.astype(np.float32), split + '_emb': emb.astype(np.float32),
+                    split + '_emb_sum': cases.checksum(emb), split + '_pc': ref_sf.compute_pc(avg, 1)})
+    save('sif_pom_full.npz', **out)
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'pom_full':
+    golden_pom_full()
+    sys.exit(0)
+
+
 if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'downstream':
     golden_downstream()
     sys.exit(0)
@@ -364,3 +388,4 @@ if __name__ == '__main__':
     golden_closed_form()
     golden_downstream()
     golden_sentiment()
+    golden_pom_full()

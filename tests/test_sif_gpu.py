@@ -297,3 +297,119 @@ def test_host_buffer_api_chunked(mods, chunk_rows):
                                             chunk_rows))
         assert abs_cos(pc[0], pc_want[0].cpu().numpy()) > 1 - 1e-9
         assert rel_err(out, want.cpu().numpy().astype(out.dtype)) < 2e-6
+
+
+@pytest.mark.parametrize('split', ['valid', 'test'])
+def test_golden_pom_full_splits(mods, golden_dir, split):
+    """BASELINE config 3 at full size: the real POM valid (100 x 1089) and test (203 x 1357) ids and the
+    real word weights, reference outputs from tests/golden/make_golden.py::golden_pom_full."""
+    nv, sf, sif = mods
+    g = np.load(os.path.join(golden_dir, 'sif_pom_full.npz'))
+    ids = g[split + '_ids'].astype(np.int64)
+    We = cases.table(7763, 300, seed=11)
+    w = sf.seq2weight(ids, np.ones(ids.shape), g['weights'])
+    np.testing.assert_array_equal(np.count_nonzero(w, axis=1), g[split + '_w_nonzero'])
+    avg = sf.get_weighted_average(We, ids, w)
+    assert rel_err(avg, g[split + '_avg'].astype(np.float64)) < EMB_RTOL
+    pc = sf.compute_pc(avg, 1)
+    assert float(np.dot(pc[0], g[split + '_pc'][0])) > PC_COS
+    emb = sif.get_sentence_embeddings(We, g['weights'], ids)
+    assert rel_err(emb, g[split + '_emb'].astype(np.float64)) < 5 * EMB_RTOL
+
+
+def test_mosi_shape_three_splits(mods):
+    """BASELINE configs 0/1, text side: MOSI-shaped splits (1284 / 229 / 686 utterances x 20 tokens,
+    3016-row table), the principal component removed per split as simplesif.py:297-299 does -- the
+    229-row split takes sklearn's transposed route (N < d), the others the plain one."""
+    nv, sf, sif = mods
+    rng = np.random.default_rng(2199)
+    We = cases.table(3016, 300, seed=3)
+    weights = None
+    for n in (1284, 229, 686):
+        ids, p = cases.zipf_ids(rng, n, 20, 3016)
+        if weights is None:
+            weights = cases.sif_weights(p)
+        got = sif.get_sentence_embeddings(We, weights, ids)
+        want = so.get_sentence_embeddings(We, weights, ids)
+        assert got.shape == (n, 300) and got.dtype == np.float64
+        assert rel_err(got, want) < 5 * EMB_RTOL, n
+
+
+def test_embed_property_random_shapes(mods):
+    """Property test (hypothesis): for random shapes, ragged lengths, duplicated / negative / padded ids
+    and weights with exact zeros, seq2weight is bit-exact and the weighted average is within tolerance
+    of the oracle; rows whose weights are all zero are NaN on both sides."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    nv, sf, sif = mods
+
+    @settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(n=st.integers(1, 70), L=st.integers(1, 130), V=st.integers(2, 300),
+           d=st.sampled_from([4, 64, 300, 512, 1024]), seed=st.integers(0, 10 ** 6),
+           p_neg=st.sampled_from([0.0, 0.05]), p_zero_w=st.sampled_from([0.0, 0.2]))
+    def check(n, L, V, d, seed, p_neg, p_zero_w):
+        rng = np.random.default_rng(seed)
+        We = rng.standard_normal((V, d)).astype(np.float32)
+        weights = rng.uniform(0.01, 1.0, V)
+        weights[rng.random(V) < p_zero_w] = 0.0
+        ids = rng.integers(0, V, size=(n, L)).astype(np.int64)
+        lens = rng.integers(0, L + 1, size=n)
+        ids[np.arange(L)[None, :] >= lens[:, None]] = 0
+        neg = rng.random(ids.shape) < p_neg
+        ids[neg] = -rng.integers(1, V + 1, size=int(neg.sum()))
+        mask = (rng.random(ids.shape) < 0.9).astype(np.float64)
+        w = sf.seq2weight(ids, mask, weights)
+        want_w = so.seq2weight(ids, mask, weights)
+        np.testing.assert_array_equal(w, want_w)
+        with np.errstate(all='ignore'):
+            want = so.get_weighted_average(We, ids, want_w)
+        got = sf.get_weighted_average(We, ids, w)
+        dead = ~np.isfinite(want).all(axis=1)
+        assert (np.isnan(got[dead]).all() if dead.any() else True)
+        if (~dead).any():
+            assert rel_err(got[~dead], want[~dead]) < EMB_RTOL
+    check()
+
+
+@pytest.mark.parametrize('V,d,L', [(3000, 300, 40), (700, 64, 33), (129, 512, 7)])
+def test_fused_lookup_equals_explicit_weights_large(mods, V, d, L):
+    """The fused kernel (weights looked up per token, mmb_sif_embed) and the explicit-weight kernel
+    (mmb_weighted_average fed with seq2weight's matrix) share one accumulation order, so at a batch large
+    enough for the persistent grid-stride loop (several utterances per warp) they must agree bit for bit
+    -- including negative ids, zero weights and an out-of-range id being reported."""
+    import torch
+    nv, sf = mods[0], mods[1]
+    lib = nv.lib
+    dev = torch.device('cuda')
+    n = 70_000
+    rng = np.random.default_rng(V + d)
+    We = cases.table(V, d, seed=V)
+    ids, p = cases.zipf_ids(rng, n, L, V)
+    weights = cases.sif_weights(p)
+    weights[rng.integers(1, V, 5)] = 0.0
+    weights[rng.integers(1, V, 5)] = rng.uniform(0, 1, 5)          # out-of-order weights
+    neg = rng.random(ids.shape) < 0.01
+    ids[neg] = -rng.integers(1, V + 1, size=int(neg.sum()))
+    t_We = torch.tensor(We, device=dev)
+    t_vw = torch.tensor(weights.astype(np.float32), device=dev)
+    t_ids = torch.tensor(ids, device=dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    hot = torch.empty((n, d), device=dev)
+    nv.check(lib.mmb_sif_embed(nv.ptr(t_We), V, d, nv.ptr(t_vw), nv.ptr(t_ids), n, L, nv.ptr(hot), nv.ptr(st),
+                               nv.stream_ptr()))
+    w = torch.empty((n, L), device=dev)
+    nv.check(lib.mmb_seq2weight(nv.ptr(t_ids), None, nv.ptr(t_vw), V, n, L, nv.ptr(w), nv.ptr(st), nv.stream_ptr()))
+    plain = torch.empty((n, d), device=dev)
+    nv.check(lib.mmb_weighted_average(nv.ptr(t_We), V, d, nv.ptr(t_ids), nv.ptr(w), n, L, nv.ptr(plain), nv.ptr(st),
+                                      nv.stream_ptr()))
+    assert int(st.item()) == 0
+    assert torch.equal(torch.nan_to_num(hot, nan=12345.0), torch.nan_to_num(plain, nan=12345.0))
+    rows = np.array([0, 1, 4242, n - 1])
+    with np.errstate(all='ignore'):
+        want = so.get_weighted_average(We, ids[rows], so.seq2weight(ids[rows], np.ones((4, L)), weights))
+    ok = np.isfinite(want).all(axis=1)
+    assert rel_err(hot[rows].double().cpu().numpy()[ok], want[ok]) < EMB_RTOL
+    # an id outside [-V, V) is still reported
+    t_ids[5, 0] = V + 3
+    nv.check(lib.mmb_sif_embed(nv.ptr(t_We), V, d, nv.ptr(t_vw), nv.ptr(t_ids), n, L, nv.ptr(hot), nv.ptr(st),
+                               nv.stream_ptr()))
+    assert int(st.item()) & nv.STATUS_BAD_INDEX
