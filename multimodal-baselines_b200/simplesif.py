@@ -89,7 +89,7 @@ def _make_optimizer(args, params, lr):
 
 def _warn_tiny_sigma(out):
     """reference simplesif.py:82-84, one device sync for all modalities instead of one each."""
-    smallest = torch.stack([d['sigma'].min() for d in out.values()]).min()
+    smallest = torch.stack([d['sigma'].detach().min() for d in out.values()]).min()
     if float(smallest.abs()) < 1e-7:
         print({m: float(d['sigma'].min()) for m, d in out.items()}, "boo!")
 
@@ -225,11 +225,9 @@ def _use_cuda_graph(args, gen_model, device):
     flag = args.get('cuda_graph', os.environ.get('MMB_CUDA_GRAPH', '0'))
     if str(flag) in ('0', 'False', 'false', ''):
         return False
-    if torch.device(device).type != 'cuda':
-        return False
-    # BatchNorm1d in training mode keeps host-visible counters; the captured step supports
-    # LayerNorm / no norm (the sweep's other half falls back to the eager loop)
-    return not isinstance(getattr(gen_model, 'norm', None), nn.BatchNorm1d)
+    # BatchNorm1d (training mode: batch statistics, running buffers and the step counter updated on the
+    # device) is captured like everything else; GraphedStep restores the buffers after its warm-up steps
+    return torch.device(device).type == 'cuda'
 
 
 def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epochs, lr, word_prob_fn,

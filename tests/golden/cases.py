@@ -159,6 +159,18 @@ OPT_CASES = {
     'adam_infer': dict(inputs=dict(B=10, T=4, d=24, A=5, Vd=4, V=30, seed=42, norm=None, unimodal=True, args={}),
                        args={'dataset': 'mosi', 'unimodal': True, 'freeze_weights': True, 'optimizer': 'adam'},
                        train=False, batch=5, epochs=3, lr=0.01),
+    # BatchNorm1d in training mode (batch statistics, running buffers updated every step): half of the
+    # reference's grid (make_configs.py:30)
+    'sgd_train_bn': dict(inputs=dict(B=12, T=5, d=24, A=6, Vd=5, V=40, seed=43, norm='batch_norm', unimodal=False,
+                                     args={}),
+                         args={'dataset': 'mosi', 'unimodal': False, 'freeze_weights': False, 'optimizer': 'sgd',
+                               'word_loss_weight': 0.2},
+                         train=True, batch=4, epochs=4, lr=0.01),
+    'adam_infer_bn': dict(inputs=dict(B=12, T=4, d=24, A=5, Vd=4, V=30, seed=44, norm='batch_norm', unimodal=False,
+                                      args={}),
+                          args={'dataset': 'mosi', 'unimodal': False, 'freeze_weights': False, 'optimizer': 'adam',
+                                'word_loss_weight': 0.1},
+                          train=False, batch=6, epochs=3, lr=0.01),
 }
 
 

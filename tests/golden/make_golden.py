@@ -372,6 +372,11 @@ if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'pom_full':
     sys.exit(0)
 
 
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'optimize_latents':
+    golden_optimize_latents()
+    sys.exit(0)
+
+
 if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'downstream':
     golden_downstream()
     sys.exit(0)

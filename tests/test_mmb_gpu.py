@@ -203,8 +203,6 @@ def test_cuda_graph_step_matches_eager_loop(mods, golden_dir, tag, shuffle):
     from torch.utils.data import DataLoader
     g = np.load(os.path.join(golden_dir, 'optimize_latents.npz'))
     cfg = cases.OPT_CASES[tag]
-    if cfg['inputs']['norm'] == 'batch_norm':
-        pytest.skip('BatchNorm1d keeps the eager loop')
     c = cases.mmb_inputs(**cfg['inputs'])
     dev = torch.device('cuda')
 
