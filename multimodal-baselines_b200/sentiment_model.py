@@ -70,8 +70,15 @@ def _index_batches(loader, device):
     global generator in the same order (num_workers = 0: the iterator's base seed first, then the
     RandomSampler's seed when the first batch is requested)."""
     torch.empty((), dtype=torch.int64).random_(generator=loader.generator)
-    for idx in loader.batch_sampler:
-        yield torch.as_tensor(idx, dtype=torch.int64).to(device, non_blocking=True)
+    batches = list(loader.batch_sampler)
+    if not batches:
+        return
+    # one host-to-device copy per pass, not one per batch
+    flat = torch.tensor([i for b in batches for i in b], dtype=torch.int64).to(device, non_blocking=True)
+    off = 0
+    for b in batches:
+        yield flat[off:off + len(b)]
+        off += len(b)
 
 
 def _l1(model, latents, labels, j):

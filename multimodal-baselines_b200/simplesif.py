@@ -217,8 +217,15 @@ def _epoch_index_batches(dataloader, device):
     the same order (num_workers = 0: one base-seed draw when the iterator is built, then the
     sampler's own draws), without collating the data sample by sample."""
     torch.empty((), dtype=torch.int64).random_(generator=dataloader.generator)
-    for idx in dataloader.batch_sampler:
-        yield torch.as_tensor(idx, dtype=torch.int64).to(device, non_blocking=True)
+    batches = list(dataloader.batch_sampler)
+    if not batches:
+        return
+    # one host-to-device copy per epoch, not one per batch
+    flat = torch.tensor([i for b in batches for i in b], dtype=torch.int64).to(device, non_blocking=True)
+    off = 0
+    for b in batches:
+        yield flat[off:off + len(b)]
+        off += len(b)
 
 
 def _use_cuda_graph(args, gen_model, device):
