@@ -236,6 +236,19 @@ MMB_API int mmb_word_ll(const float* latents, int B, int d, const float* table, 
                 int64_t tmask_stride_t, int L, float a, float* lp, float* grad, void* ws,
                 size_t ws_bytes, int* status, mmb_stream_t stream);
 
+/* The same term when the token vectors are rows of `table` (reference simplesif.py:319-340 builds
+ * text = word_embeddings[ids]): ids (B, L) int64, row b at ids + b*ids_stride_b, replace
+ * `sent`.  The token cosines are read out of the (B, V) cosine matrix of the partition term and the token
+ * gradient rides its (B, V) x (V, d) product, so no (B, L, d) tensor is read: the cost is independent of
+ * L*d.  tmask may be NULL (= ids != 0).  Ids outside [0, V) set MMB_STATUS_BAD_INDEX.  Needs
+ * (V + L) * 4 bytes of shared memory per utterance (<= 200 KiB), else MMB_E_UNSUPPORTED.
+ *   ws >= mmb_word_ll_ids_workspace_bytes(B, V, d).                                                    */
+MMB_API size_t mmb_word_ll_ids_workspace_bytes(int B, int64_t V, int d);
+MMB_API int mmb_word_ll_ids(const float* latents, int B, int d, const float* table, const float* inv_norm,
+                    int64_t V, const int64_t* ids, int64_t ids_stride_b, const float* word_w,
+                    const float* tmask, int64_t tmask_stride_b, int64_t tmask_stride_t, int L, float a,
+                    float* lp, float* grad, void* ws, size_t ws_bytes, int* status, mmb_stream_t stream);
+
 /* ---------------------------------------------------------------- closed form (N1) */
 /* estimate_embedding_overall_gpu2 -- sif2.py:164-208 with calc_weights sif2.py:103-114 (call site
  * simplesif.py:808-880): gradient-free latents as the weight-normalised, L2-normalised sum of the

@@ -325,7 +325,7 @@ constexpr float kInvPi = 0.3183098861837907f;
 __global__ void __launch_bounds__(256)
     word_cos_kernel(const float* __restrict__ e, const float* __restrict__ ie, int B, int d,
                     const float* __restrict__ W, const float* __restrict__ iw, int V, float* __restrict__ S,
-                    float* __restrict__ Hw, float* __restrict__ Q) {
+                    float* __restrict__ Hw, float* __restrict__ Q, float* __restrict__ Cos = nullptr) {
   __shared__ TileSmem sm;
   const int n0 = blockIdx.x * kTN, m0 = blockIdx.y * kTM;
   float acc[4][4];
@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(256)
       S[(size_t)m * V + n] = 1.f - acosf(c) * kInvPi;
       Hw[(size_t)m * V + n] = h * iwn;
       Q[(size_t)m * V + n] = h * c;
+      if (Cos) Cos[(size_t)m * V + n] = c;
     }
   }
 }
@@ -461,6 +462,110 @@ __global__ void __launch_bounds__(256)
     for (int t = 0; t < L; ++t) tok = fmaf(r_t[t], __ldg(sent + (size_t)b * s_sb + (size_t)t * s_st + k), tok);
     grad[(size_t)b * d + k] = (g + tok) * inv_e;
   }
+}
+
+// ---- word term from token IDS -------------------------------------------------
+// When the token vectors are rows of the word table itself (reference simplesif.py:319-340 builds
+// `text = word_embeddings[ids]`), everything the per-token part needs is already in the (B, V) matrices
+// of the partition term: the token's cosine is Cos[b][id], its inverse norm is iw[id], and its share of
+// the gradient, r_t * w_hat_{id}, is one more entry of the (B, V) coefficient matrix that multiplies the
+// table in the gradient product.  No (B, L, d) tensor is read or even exists; the cost no longer
+// depends on L * d (POM: L = 1357).
+//
+// One CTA per utterance.  M[b][v] = DZ_b * Hw[b][v] + sum_{t: id_t = v} r_t * iw[v] is assembled in shared
+// memory; the token contributions are added by ONE warp in token order, duplicates inside a 32-token
+// chunk merged with match.any and a fixed butterfly -> deterministic.  aux[b] = DZ_b * HC_b + RC_b.
+__global__ void __launch_bounds__(256)
+    word_token_ids_kernel(int B, int V, const float* __restrict__ S, const float* __restrict__ Q,
+                          const float* __restrict__ Cos, float* __restrict__ HwM, const float* __restrict__ iw,
+                          const int64_t* __restrict__ ids, int64_t ids_sb, const float* __restrict__ word_w,
+                          const float* __restrict__ tmask, int64_t m_sb, int64_t m_st, int L, float a,
+                          float* __restrict__ lp, float* __restrict__ aux, int* __restrict__ status) {
+  extern __shared__ float dyn[];   // V floats: row of M; then L floats: r_t * iw
+  __shared__ float red[8];
+  float* Mrow = dyn;
+  float* r_t = dyn + V;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float z = 0.f, hc = 0.f;
+  for (int v = tid; v < V; v += 256) {
+    z += S[(size_t)b * V + v];
+    hc += Q[(size_t)b * V + v];
+  }
+  const float Z = block_sum(z, red);
+  const float HC = block_sum(hc, red);
+  const float alpha = 1.f / (Z * a + 1.f);
+  float lp_acc = 0.f, dz_acc = 0.f, rc_acc = 0.f;
+  bool bad = false;
+  for (int t = tid; t < L; t += 256) {
+    const int64_t id = ids[(size_t)b * ids_sb + t];
+    float rw = 0.f;
+    if (id >= 0 && id < V) {
+      const float c = Cos[(size_t)b * V + id];
+      const float st = S[(size_t)b * V + id];
+      const float w = word_w[(size_t)b * L + t];
+      const float mk = tmask ? tmask[(size_t)b * m_sb + (size_t)t * m_st] : (id != 0 ? 1.f : 0.f);
+      const float p = alpha * w + (1.f - alpha) * st / Z;
+      lp_acc += logf(p) * mk;
+      const float dlp_dp = mk / p;
+      const float dp_dZ = (-a * alpha * alpha) * (w - st / Z) - (1.f - alpha) * st / (Z * Z);
+      dz_acc += dlp_dp * dp_dZ;
+      const float rr = dlp_dp * (1.f - alpha) / Z * (kInvPi / sqrtf(1.f - c * c));
+      rc_acc += rr * c;
+      rw = rr * iw[id];
+    } else {
+      bad = true;
+    }
+    r_t[t] = rw;
+  }
+  const float LP = block_sum(lp_acc, red);
+  const float DZ = block_sum(dz_acc, red);
+  const float RC = block_sum(rc_acc, red);
+  for (int v = tid; v < V; v += 256) Mrow[v] = DZ * HwM[(size_t)b * V + v];
+  __syncthreads();
+  if (warp == 0) {
+    for (int t0 = 0; t0 < L; t0 += 32) {
+      const int t = t0 + lane;
+      int64_t id = -1;
+      float val = 0.f;
+      if (t < L) {
+        id = ids[(size_t)b * ids_sb + t];
+        if (id < 0 || id >= V) id = -1;
+        else val = r_t[t];
+      }
+      const int key = (int)id;
+      const unsigned grp = __match_any_sync(0xffffffffu, key);
+      const bool head = key >= 0 && lane == __ffs(grp) - 1;
+      unsigned multi = __ballot_sync(0xffffffffu, head && (grp & (grp - 1u)));
+      while (multi) {
+        const int j = __ffs(multi) - 1;
+        multi &= multi - 1u;
+        const unsigned gj = __shfl_sync(0xffffffffu, grp, j);
+        const float sum = warp_sum(((gj >> lane) & 1u) ? val : 0.f);
+        if (lane == j) val = sum;
+      }
+      if (head) Mrow[key] += val;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int v = tid; v < V; v += 256) HwM[(size_t)b * V + v] = Mrow[v];
+  if (tid == 0) {
+    lp[b] = LP;
+    aux[b] = DZ * HC + RC;
+    if (!isfinite(LP)) atomicOr(status, MMB_STATUS_NONFINITE);
+  }
+  if (bad) atomicOr(status, MMB_STATUS_BAD_INDEX);
+}
+
+// grad[b][k] = (G[b][k] - aux[b] * e[b][k] * ie[b]) * ie[b]
+__global__ void __launch_bounds__(256)
+    word_grad_finish_kernel(const float* __restrict__ G, const float* __restrict__ e, const float* __restrict__ ie,
+                            const float* __restrict__ aux, int B, int d, float* __restrict__ grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * d) return;
+  const int b = i / d;
+  const float inv_e = ie[b];
+  grad[i] = (G[i] - aux[b] * e[i] * inv_e) * inv_e;
 }
 
 }  // namespace mmb
@@ -660,5 +765,57 @@ extern "C" int mmb_word_ll(const float* latents, int B, int d, const float* tabl
                                                           sent_stride_b, sent_stride_t, word_w, tmask,
                                                           tmask_stride_b, tmask_stride_t, L, a, lp, grad, status);
   MMB_LAUNCH_CHECK("word_finish");
+  return MMB_OK;
+}
+
+extern "C" size_t mmb_word_ll_ids_workspace_bytes(int B, int64_t V, int d) {
+  // S, Hw/M, Q, Cos: (B, V) each; G: (B, d); ie, aux: (B) each; split-K partials of G: (splits, B, d)
+  return ((size_t)4 * B * V + (size_t)B * d + 2 * (size_t)B + (size_t)word_h_splits(V) * B * d) * sizeof(float) + 256;
+}
+
+extern "C" int mmb_word_ll_ids(const float* latents, int B, int d, const float* table, const float* inv_norm,
+                               int64_t V, const int64_t* ids, int64_t ids_stride_b, const float* word_w,
+                               const float* tmask, int64_t tmask_stride_b, int64_t tmask_stride_t, int L,
+                               float a, float* lp, float* grad, void* ws, size_t ws_bytes, int* status,
+                               mmb_stream_t stream) {
+  MMB_REQUIRE(latents && table && inv_norm && ids && word_w && lp && grad && ws && status, "null pointer");
+  MMB_REQUIRE(B > 0 && d > 0 && V > 0 && L > 0 && V < (1 << 30), "bad size");
+  MMB_REQUIRE(ws_bytes >= mmb_word_ll_ids_workspace_bytes(B, V, d), "workspace too small");
+  const size_t smem = ((size_t)V + (size_t)L) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("mmb_word_ll_ids: vocabulary row + tokens (%zu bytes) exceed shared memory; use mmb_word_ll", smem);
+    return MMB_E_UNSUPPORTED;
+  }
+  cudaStream_t st = as_stream(stream);
+  float* S = (float*)ws;
+  float* Hw = S + (size_t)B * V;
+  float* Q = Hw + (size_t)B * V;
+  float* Cos = Q + (size_t)B * V;
+  float* G = Cos + (size_t)B * V;
+  float* ie = G + (size_t)B * d;
+  float* aux = ie + B;
+  float* hpart = aux + B;
+  row_inv_norm_kernel<<<(B + 7) / 8, 256, 0, st>>>(latents, B, d, ie);
+  MMB_LAUNCH_CHECK("row_inv_norm(latents)");
+  dim3 g1((unsigned)((V + kTN - 1) / kTN), (B + kTM - 1) / kTM);
+  word_cos_kernel<<<g1, 256, 0, st>>>(latents, ie, B, d, table, inv_norm, (int)V, S, Hw, Q, Cos);
+  MMB_LAUNCH_CHECK("word_cos");
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMB_CUDA(cudaFuncSetAttribute(word_token_ids_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  word_token_ids_kernel<<<B, 256, smem, st>>>(B, (int)V, S, Q, Cos, Hw, inv_norm, ids, ids_stride_b, word_w, tmask,
+                                              tmask_stride_b, tmask_stride_t, L, a, lp, aux, status);
+  MMB_LAUNCH_CHECK("word_token_ids");
+  const int splits = word_h_splits(V);
+  const int vchunk = (int)(((V + splits - 1) / splits + kTK - 1) / kTK * kTK);
+  dim3 g2((d + kTN - 1) / kTN, (B + kTM - 1) / kTM, (unsigned)((V + vchunk - 1) / vchunk));
+  word_h_kernel<<<g2, 256, 0, st>>>(Hw, table, B, (int)V, d, vchunk, hpart);
+  MMB_LAUNCH_CHECK("word_h");
+  splitk_reduce_kernel<<<(B * d + 255) / 256, 256, 0, st>>>(hpart, (int)g2.z, B * d, G);
+  MMB_LAUNCH_CHECK("word_h_reduce");
+  word_grad_finish_kernel<<<(B * d + 255) / 256, 256, 0, st>>>(G, latents, ie, aux, B, d, grad);
+  MMB_LAUNCH_CHECK("word_grad_finish");
   return MMB_OK;
 }

@@ -28,9 +28,50 @@ class CatSegments(object):
         return torch.cat(self.parts, dim=-1)
 
 
+class TokenIds(object):
+    """Token vectors that are never materialised: what ``word_embeddings[ids]`` (reference
+    simplesif.py:319-340) denotes, kept as the (B, L) int64 ids and the table they index.
+    ``get_word_log_prob_angular2`` accepts it as ``sent_embeddings`` and then reads no (B, L, d) tensor at
+    all; anything else can ``materialize()`` it."""
+
+    def __init__(self, ids, table):
+        self.ids, self.table = ids, table
+
+    @property
+    def shape(self):
+        return tuple(self.ids.shape) + (self.table.shape[-1],)
+
+    @property
+    def device(self):
+        return self.ids.device
+
+    def __len__(self):
+        return self.ids.shape[0]
+
+    def __getitem__(self, idx):
+        return TokenIds(self.ids[idx], self.table)
+
+    def size(self):
+        return torch.Size(self.shape)
+
+    def materialize(self):
+        return self.table[self.ids]
+
+    def mask(self):
+        """update_masks (reference simplesif.py:36-40): ids != 0 broadcast over the feature axis."""
+        m = (self.ids != 0).to(torch.float32)
+        return m[:, :, None].expand(*self.shape)
+
+
 def _segments(values, mask):
     v = values.parts if isinstance(values, CatSegments) else [values]
     k = mask.parts if isinstance(mask, CatSegments) else [mask]
+    if len(v) == len(k):
+        # a TokenIds part of a Gaussian modality is expanded for this batch only (B x T x d); its mask may
+        # be the per-token (B, T) form
+        k = [(x.mask() if m is None else m[:, :, None].expand(*x.shape) if m.dim() == 2 else m)
+             if isinstance(x, TokenIds) else m for x, m in zip(v, k)]
+    v = [x.materialize() if isinstance(x, TokenIds) else x for x in v]
     if len(v) != len(k):
         v, k = [torch.cat(v, -1)], [torch.cat(k, -1)]
     return list(zip(v, k))
@@ -87,6 +128,18 @@ def get_word_log_prob_angular2(latents, word_embeddings, word_weights, sent_embe
     mask (B, L, d) (only ``mask[:, :, 0]`` is used, line 90) or (B, L).  Returns (B,).
     """
     status = mmb_ops.new_status(latents.device)
+    if isinstance(sent_embeddings, TokenIds):
+        same_table = (sent_embeddings.table.data_ptr() == word_embeddings.data_ptr()
+                      and sent_embeddings.table.shape == word_embeddings.shape)
+        V, L = word_embeddings.shape[0], sent_embeddings.ids.shape[1]
+        if same_table and (V + L) * 4 <= 200 * 1024:
+            if mask is not None and mask.dim() == 3:
+                mask = mask[:, :, 0]
+            return mmb_ops.WordLLIdsFunction.apply(latents, word_embeddings, word_weights, sent_embeddings.ids,
+                                                   mask, a, status)
+        if mask is None:
+            mask = sent_embeddings.mask()
+        sent_embeddings = sent_embeddings.materialize()
     return mmb_ops.WordLLFunction.apply(latents, word_embeddings, word_weights, sent_embeddings, mask, a, status)
 
 

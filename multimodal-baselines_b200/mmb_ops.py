@@ -200,6 +200,46 @@ class WordLLFunction(torch.autograd.Function):
         return g.unsqueeze(1) * grad, None, None, None, None, None, None
 
 
+class WordLLIdsFunction(torch.autograd.Function):
+    """The same term when the token vectors are rows of the word table: ids (B, L) int64 instead of the
+    (B, L, d) vectors (``mmb_word_ll_ids``).  ``mask`` is (B, L) float or None (= ids != 0)."""
+
+    @staticmethod
+    def forward(ctx, latents, table, word_w, ids, mask, a, status):
+        e = _f32(latents)
+        table = _f32(table)
+        word_w = _f32(word_w)
+        if not ids.is_cuda or ids.dtype != torch.int64:
+            raise nv.MMBError('token ids must be an int64 CUDA tensor')
+        if ids.stride(-1) != 1:
+            ids = ids.contiguous()
+        B, d = e.shape
+        V = table.shape[0]
+        L = word_w.shape[1]
+        if tuple(ids.shape) != (B, L) or (mask is not None and tuple(mask.shape[:2]) != (B, L)):
+            raise RuntimeError('word term: shapes do not match (latents %s, ids %s, weights %s)'
+                               % (tuple(e.shape), tuple(ids.shape), tuple(word_w.shape)))
+        if mask is not None and not (mask.dtype == torch.float32 and mask.is_cuda):
+            mask = _f32(mask)
+        inv_norm = table_inv_norm(table)
+        lp = torch.empty(B, dtype=torch.float32, device=e.device)
+        grad = torch.empty_like(e)
+        nbytes = lib.mmb_word_ll_ids_workspace_bytes(B, V, d)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=e.device)
+        nv.check(lib.mmb_word_ll_ids(nv.ptr(e), B, d, nv.ptr(table), nv.ptr(inv_norm), V, nv.ptr(ids), ids.stride(0),
+                                     nv.ptr(word_w), C.c_void_p(mask.data_ptr()) if mask is not None else None,
+                                     mask.stride(0) if mask is not None else 0,
+                                     mask.stride(1) if mask is not None else 0, L, float(a), nv.ptr(lp),
+                                     nv.ptr(grad), nv.ptr(ws), nbytes, nv.ptr(status), nv.stream_ptr()))
+        ctx.save_for_backward(grad)
+        return lp
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return g.unsqueeze(1) * grad, None, None, None, None, None, None
+
+
 _STATUS_SINK = None
 _INV_NORM_CACHE = {}
 

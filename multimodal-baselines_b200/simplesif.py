@@ -26,12 +26,12 @@ import torch.nn as nn
 import torch.optim as optim
 from torch.utils.data import DataLoader
 
-from losses import CatSegments, get_log_prob_matrix, get_word_log_prob_angular, get_word_log_prob_dot_prod  # noqa: F401
+from losses import CatSegments, TokenIds, get_log_prob_matrix, get_word_log_prob_angular, get_word_log_prob_dot_prod  # noqa: F401
 from losses import get_word_log_prob_angular2
 from models import AudioVisualGeneratorConcat, AudioVisualGenerator, AudioVisualGeneratorMultimodal  # noqa: F401
 from sentiment_model import SentimentData, SentimentModel, train_sentiment_for_latents
 from sif import load_weights, get_sentence_embeddings
-from utils import load_data, normalize_data, MMData, MMDataExtra, add_positional_embeddings
+from utils import load_data, normalize_data, MMData, MMDataExtra, MMDataIds, MMDataExtraIds, add_positional_embeddings
 
 try:  # not part of the reference tree either
     from analyze_embeddings import get_closest_words
@@ -53,14 +53,18 @@ def update_masks_vect(mask_dict, data, key='text'):
     mask_dict[key] = np.broadcast_to(np.expand_dims(tmp2, -1), data.shape)
 
 
-def _batch_dicts(args, x):
+def _batch_dicts(args, x, table=None):
     """The per-step ``batch_data`` / ``batch_masks`` of reference simplesif.py:72-124, with the
-    concatenated modalities expressed as CatSegments instead of materialised torch.cat."""
+    concatenated modalities expressed as CatSegments instead of materialised torch.cat.  A batch of an
+    id-based dataset (``MMDataIds``: int64 ids in the text slot) is wrapped as ``TokenIds(ids, table)``."""
     if args['dataset'] == 'mosi':
         j, text, aud, vis, text_m, aud_m, vis_m, text_w = x
-        text_gauss, text_gauss_m = text, text_m
     else:
         j, text, aud, vis, text_m, aud_m, vis_m, text_w, text_gauss, text_gauss_m = x
+    if torch.is_tensor(text) and text.dtype == torch.int64:
+        text = TokenIds(text, table)
+    if args['dataset'] == 'mosi':
+        text_gauss, text_gauss_m = text, text_m
     batch_data = {'text': text, 'audio': aud, 'visual': vis, 'text_weights': text_w}
     batch_masks = {'text': text_m, 'audio': aud_m, 'visual': vis_m}
     if not args['unimodal']:
@@ -123,11 +127,14 @@ class GraphedStep(object):
         names = ['text', 'audio', 'visual', 'text_mask', 'audio_mask', 'visual_mask', 'text_weights']
         if hasattr(ds, 'text_aligned'):
             names += ['text_aligned', 'text_aligned_mask']
+        if hasattr(ds, 'text_ids'):      # id-based dataset: the text slot is an int64 gather of (B, L) ids
+            got = self.mmb_ops.gather_multi([getattr(ds, n) for n in names[1:]], j)
+            return (j, ds.text_ids[j]) + tuple(got)
         return (j,) + tuple(self.mmb_ops.gather_multi([getattr(ds, n) for n in names], j))
 
     def _step(self, j):
         x = self._gather(j)                       # batched gather of the device-resident tensors
-        _, batch_data, batch_masks = _batch_dicts(self.args, x)
+        _, batch_data, batch_masks = _batch_dicts(self.args, x, getattr(self.dataset, 'table', None))
         e = self.embeddings[j]
         out = self.gen_model(e)
         log_prob = -get_log_prob_matrix(self.args, e, out, batch_data, batch_masks, self.word_prob_fn,
@@ -276,7 +283,7 @@ def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epoc
             stepper.check()
         else:
             for x in dataloader:
-                j, batch_data, batch_masks = _batch_dicts(args, x)
+                j, batch_data, batch_masks = _batch_dicts(args, x, getattr(dataloader.dataset, 'table', None))
                 iters += 1
                 optimizer.zero_grad()
                 out = gen_model(embeddings[j])
@@ -370,7 +377,7 @@ def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, 
             stepper.check()
         else:
             for x in dataloader:
-                j, batch_data, batch_masks = _batch_dicts(args, x)
+                j, batch_data, batch_masks = _batch_dicts(args, x, getattr(dataloader.dataset, 'table', None))
                 iters += 1
                 optimizer.zero_grad()
                 out = gen_model(train_embed[j])
@@ -461,8 +468,13 @@ def prepare_splits(args, word_embeddings, weights, splits, masks, device):
         else:
             s['text_align'] = s['text']
             update_masks_vect(m, s['text_align'], 'text_align')
-        s['text'] = we_t[ids]
-        s['text_weights'] = w_t[ids]
+        if args.get('text_ids'):
+            # keep the transcript as ids; run_experiment builds MMDataIds from them
+            s['text'] = TokenIds(ids, we_t)
+            s['text_weights'] = w_t
+        else:
+            s['text'] = we_t[ids]
+            s['text_weights'] = w_t[ids]
         if args.get('pos_embed_dim', 0) and args['pos_embed_dim'] > 0:
             n_points, seq_len = m['covarep'].shape[:2]
             ext = np.ones((n_points, seq_len, args['pos_embed_dim']), dtype=np.int64)
@@ -483,6 +495,12 @@ def run_experiment(args, word_embeddings, weights, splits, masks, device, folder
     train, valid, test = splits
 
     def dataset(s, m):
+        if isinstance(s['text'], TokenIds):
+            t = s['text']
+            if args['dataset'] == 'mosi':
+                return MMDataIds(t.ids, s['covarep'], s['facet'], m, s['text_weights'], t.table, device)
+            return MMDataExtraIds(t.ids, s['covarep'], s['facet'], m, s['text_weights'], t.table, s['text_align'],
+                                  device)
         if args['dataset'] == 'mosi':
             return MMData(s['text'], s['covarep'], s['facet'], m, s['text_weights'], device)
         return MMDataExtra(s['text'], s['covarep'], s['facet'], m, s['text_weights'], s['text_align'], device)

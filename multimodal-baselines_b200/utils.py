@@ -131,6 +131,47 @@ class MMData(Dataset):
                 self.audio_mask[idx], self.visual_mask[idx], self.text_weights[idx])
 
 
+class MMDataIds(Dataset):
+    """``MMData`` without the (N, L, d) word-vector tensor and its (N, L, d) mask: the text
+    is kept as the (N, L) int64 ids + the table they index (``losses.TokenIds``), the text mask as the (N, L)
+    ``ids != 0`` and the per-token weights as ``vocab_weights[ids]``.  ``__getitem__`` returns the same tuple
+    positions as ``MMData`` (reference utils.py:231-233) with the ids in the text slot; the word term then runs
+    from the ids alone."""
+
+    def __init__(self, text_ids, audio, visual, masks, vocab_weights, table, device):
+        super(Dataset, self).__init__()
+        self.text_ids = torch.as_tensor(np.asarray(text_ids) if not torch.is_tensor(text_ids) else text_ids,
+                                        dtype=torch.int64).to(device)
+        self.table = _as_f32(table, device)
+        self.audio, self.visual = _as_f32(audio, device), _as_f32(visual, device)
+        self.text_weights = _as_f32(vocab_weights, device)[self.text_ids]
+        self.text_mask = (self.text_ids != 0).to(torch.float32)
+        self.audio_mask, self.visual_mask = _as_f32(masks['covarep'], device), _as_f32(masks['facet'], device)
+        assert self.text_ids.size()[0] == self.audio.size()[0] == self.visual.size()[0]
+        self.len = self.text_ids.size()[0]
+
+    def __len__(self):
+        return self.len
+
+    def __getitem__(self, idx):
+        # position 1 carries the ids (int64); the loops wrap them as losses.TokenIds(ids, self.table)
+        return (idx, self.text_ids[idx], self.audio[idx], self.visual[idx],
+                self.text_mask[idx], self.audio_mask[idx], self.visual_mask[idx], self.text_weights[idx])
+
+
+class MMDataExtraIds(MMDataIds):
+    """``MMDataExtra`` (reference utils.py:235-251) with the unaligned transcript as ids; the aligned word
+    vectors that feed the Gaussian terms stay dense."""
+
+    def __init__(self, text_ids, audio, visual, masks, vocab_weights, table, text_aligned, device):
+        super(MMDataExtraIds, self).__init__(text_ids, audio, visual, masks, vocab_weights, table, device)
+        self.text_aligned = _as_f32(text_aligned, device)
+        self.text_aligned_mask = _as_f32(masks['text_align'], device)
+
+    def __getitem__(self, idx):
+        return MMDataIds.__getitem__(self, idx) + (self.text_aligned[idx], self.text_aligned_mask[idx])
+
+
 class MMDataExtra(MMData):
     """reference utils.py:235-251 -- adds the aligned text vectors + mask (POM / IEMOCAP)."""
 

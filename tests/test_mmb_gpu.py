@@ -112,6 +112,74 @@ def test_word_term_value_and_grad(mods, golden_dir, tag):
     assert torch.allclose(lp2, lp.detach())
 
 
+@pytest.mark.parametrize('tag', list(cases.MMB_CASES))
+def test_word_term_from_token_ids(mods, golden_dir, tag):
+    """the word term fed with ids + table (losses.TokenIds) instead of the (B, L, d) word
+    vectors -- value and gradient against the reference golden and against the dense path; then the whole
+    step (get_log_prob_matrix, text as TokenIds also inside the Gaussian modalities) against the golden."""
+    torch, losses, models = mods
+    g = np.load(os.path.join(golden_dir, 'mmb_%s.npz' % tag))
+    cfg, c, t, model, data, masks = build(torch, models, losses, tag, True)
+    ids = torch.tensor(c['ids'], device='cuda')
+    tok = losses.TokenIds(ids, t['We'])
+    assert tok.shape == tuple(t['text'].shape) and torch.equal(tok.materialize(), t['text'])
+    for mask in (t['text_m'], t['text_m'][:, :, 0].contiguous(), None):     # (B,L,d), (B,L), ids != 0
+        lat = t['latents'].clone().requires_grad_(True)
+        lp = losses.get_word_log_prob_angular2(lat, t['We'], t['text_w'], tok, mask, 1e-3)
+        close(lp.detach().cpu(), g['word_lp'], VAL_RTOL, 'word_lp')
+        lp.sum().backward()
+        close(lat.grad.cpu(), g['word_grad'], GRAD_RTOL, 'word_grad')
+    # a different table object -> the dense kernel on the expanded vectors, same numbers
+    lp_d = losses.get_word_log_prob_angular2(t['latents'], t['We'].clone(), t['text_w'], tok, None, 1e-3)
+    close(lp_d.cpu(), g['word_lp'], VAL_RTOL, 'word_lp dense fallback')
+    # whole step
+    m2 = t['text_m'][:, :, 0].contiguous()
+    data['text'], masks['text'] = tok, m2
+    if not cfg['unimodal']:
+        C = losses.CatSegments
+        data.update(textaudio=C([tok, t['aud']]), textvisual=C([tok, t['vis']]), textaudiovisual=C([tok, t['aud'], t['vis']]))
+        masks.update(textaudio=C([m2, t['aud_m']]), textvisual=C([m2, t['vis_m']]),
+                     textaudiovisual=C([m2, t['aud_m'], t['vis_m']]))
+    lat = t['latents'].clone().requires_grad_(True)
+    total = losses.get_log_prob_matrix(dict(cfg['args']), lat, model(lat), data, masks,
+                                       lambda l, w, s, m: losses.get_word_log_prob_angular2(l, t['We'], w, s, m, 1e-3))
+    close(total.detach().cpu(), g['total'], VAL_RTOL, 'total')
+    (-total).mean().backward()
+    close(lat.grad.cpu(), g['grad_latents'], GRAD_RTOL, 'grad_latents')
+
+
+def test_word_term_ids_long_transcripts(mods):
+    """POM-sized transcripts (L = 1357, V = 7763; heavy repetition of ids inside an utterance, padding,
+    an out-of-range id): ids path == dense path, deterministic, bad index reported."""
+    torch, losses, models = mods
+    import mmb_ops
+    dev = torch.device('cuda')
+    gen = torch.Generator(device='cpu').manual_seed(5)
+    B, L, V, d = 9, 1357, 7763, 300
+    We = (0.4 * torch.randn(V, d, generator=gen) + 0.3 * torch.randn(1, d, generator=gen)).to(dev)
+    ids = (torch.rand(B, L, generator=gen).pow(4.0) * (V - 1)).long() + 1       # skewed: many repeats
+    lens = torch.randint(50, L + 1, (B, 1), generator=gen)
+    ids[torch.arange(L)[None, :] >= lens] = 0
+    ids = ids.to(dev)
+    w = (torch.rand(B, L, generator=gen) * 0.9 + 0.1).to(dev)
+    e = (We[ids] * w[:, :, None]).sum(1) / L + 0.01 * torch.randn(B, d, generator=gen).to(dev)
+    tok = losses.TokenIds(ids, We)
+    res = []
+    for sent in (tok, tok, We[ids]):
+        lat = e.clone().requires_grad_(True)
+        lp = losses.get_word_log_prob_angular2(lat, We, w, sent, (ids != 0).float(), 1e-3)
+        lp.sum().backward()
+        res.append((lp.detach(), lat.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])          # deterministic
+    close(res[0][0].cpu(), res[2][0].cpu(), 1e-5, 'lp ids vs dense')
+    close(res[0][1].cpu(), res[2][1].cpu(), 2e-4, 'grad ids vs dense')
+    bad = ids.clone()
+    bad[3, 7] = V + 5
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    mmb_ops.WordLLIdsFunction.apply(e, We, w, bad, None, 1e-3, st)
+    assert int(st.item()) & 1
+
+
 def test_frozen_heads_and_latent_only_grads(mods):
     """optimize_latents(train=False) / freeze_weights: only the latents receive gradients."""
     torch, losses, models = mods
@@ -312,13 +380,13 @@ THIRD_DECIMAL = 1e-3     # |metric - reference metric| stays below one unit of t
 
 
 @pytest.mark.parametrize('tag', sorted(cases.DOWNSTREAM_CASES))
-@pytest.mark.parametrize('graph', [0, 1])
-def test_downstream_metrics(mods, golden_dir, tag, graph, capsys):
+@pytest.mark.parametrize('graph,text_ids', [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_downstream_metrics(mods, golden_dir, tag, graph, text_ids, capsys):
     torch = mods[0]
     import simplesif
     cfg = cases.DOWNSTREAM_CASES[tag]
     g = np.load(os.path.join(golden_dir, 'downstream.npz'))
-    args = dict(cfg['args'], cuda_graph=graph)
+    args = dict(cfg['args'], cuda_graph=graph, text_ids=text_ids)   # text_ids: transcripts kept as ids (N3)
     We, weights, splits, masks = cases.downstream_inputs(**cfg)
     dev = torch.device('cuda')
     torch.manual_seed(cfg['seed'])
