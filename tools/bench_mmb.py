@@ -57,7 +57,7 @@ def synth(name, device, seed=0):
     latents = (text * text_w[:, :, None]).sum(1) / T
     to = lambda t: t.to(device)
     out = dict(table=to(table), text=to(text), text_m=to(text_m), aud=to(aud), aud_m=to(aud_m), vis=to(vis),
-               vis_m=to(vis_m), text_w=to(text_w), latents=to(latents), dims=(Ad, Vd), N=N)
+               vis_m=to(vis_m), text_w=to(text_w), latents=to(latents), dims=(Ad, Vd), N=N, ids=to(ids))
     if name == 'pom_real':
         L = L_UNALIGNED
         ids_u = torch.randint(1, V, (N, L), generator=g)
@@ -185,14 +185,19 @@ def run(name, steps, do_cpu, only_ours=False):
     ms_graph, l_graph = time_gpu(lambda i: stepper(perm[(i % n_batches) * B:(i % n_batches + 1) * B]), steps)
     stepper.check()
     ids_arm = None
-    if 'ids_u' in S:
-        # the transcript as ids (no (N, 1357, 300) tensors), word term from the ids alone
-        ds_i = utils.MMDataExtraIds(S['ids_u'], S['aud'], S['vis'], dict(mk, text_align=S['text_a_m']),
-                                    torch.ones(S['table'].shape[0], device=dev), S['table'], S['text_a'], dev)
+    if True:
+        # the transcript as ids (no (N, L, 300) tensors), word term from the ids alone
+        ones = torch.ones(S['table'].shape[0], device=dev)
+        if 'ids_u' in S:
+            ds_i = utils.MMDataExtraIds(S['ids_u'], S['aud'], S['vis'], dict(mk, text_align=S['text_a_m']), ones,
+                                        S['table'], S['text_a'], dev)
+        else:
+            ds_i = utils.MMDataIds(S['ids'], S['aud'], S['vis'], mk, ones, S['table'], dev)
         ds_i.text_weights = S['text_w']
         lat_i = S['latents'].clone().requires_grad_(True)
         opt_i = torch.optim.SGD([lat_i] + list(model.parameters()), lr=1e-7)
-        st_i = simplesif.GraphedStep({'dataset': 'pom', 'unimodal': False}, model, lat_i, ds_i, opt_i, word_fn, dev)
+        st_i = simplesif.GraphedStep({'dataset': 'pom' if 'ids_u' in S else 'mosi', 'unimodal': False}, model, lat_i,
+                                     ds_i, opt_i, word_fn, dev)
         ms_i, l_i = time_gpu(lambda i: st_i(perm[(i % n_batches) * B:(i % n_batches + 1) * B]), steps)
         st_i.check()
         ids_arm = {'ms_per_step': ms_i, 'value': B / ms_i * 1e3, 'loss': l_i}
