@@ -219,6 +219,19 @@ MMB_API int mmb_gauss_ll(int B, int T, int n_mod, const int* n_seg, const float*
                  const float* const* sigma, float* lp, float* const* dmu, float* const* dsigma,
                  int* status, mmb_stream_t stream);
 
+/* The same likelihood from per-utterance moments.  An utterance's data does not change between
+ * optimisation steps (only mu and sigma do), so the sums over time are taken ONCE per dataset:
+ *   mmb_gauss_moments: val, mask (N, T, F) -> stats (N, 3, F) = [S0 = sum_t m | mean = sum_t m x / S0 |
+ *   M2 = sum_t m (x - mean)^2] (S0 = 0 gives mean = M2 = 0);
+ *   mmb_gauss_ll_stats: mmb_gauss_ll with seg_stats[s] = the (B, 3, seg_F[s]) moments of the batch rows in
+ *   place of seg_val / seg_mask, using  sum_t m (x - mu)^2 = M2 + S0 (mean - mu)^2  (exact, cancellation-free):
+ *   3 floats per (utterance, feature) per step instead of 2 T.                                            */
+MMB_API int mmb_gauss_moments(const float* val, const float* mask, int64_t N, int T, int F, float* stats,
+                      mmb_stream_t stream);
+MMB_API int mmb_gauss_ll_stats(int B, int n_mod, const int* n_seg, const float* const* seg_stats, const int* seg_F,
+                       const float* const* mu, const float* const* sigma, float* lp, float* const* dmu,
+                       float* const* dsigma, int* status, mmb_stream_t stream);
+
 /* get_word_log_prob_angular2 -- losses.py:68-95, value + d/d latents (Appendix A.5).
  *   latents (B, d); table (V, d) and inv_norm (V) = 1/max(||row||, 1e-8) from
  *   mmb_row_inv_norm (torch CosineSimilarity's clamp); sent: token vectors, element

@@ -71,6 +71,8 @@ SIGNATURES = {
     'mmb_word_ll_workspace_bytes': (_sz, [_i, _i64, _i]),
     'mmb_word_ll': (_i, [_p, _i, _i, _p, _p, _i64, _p, _i64, _i64, _p, _p, _i64, _i64, _i, _f, _p, _p,
                          _p, _sz, _p, _p]),
+    'mmb_gauss_moments': (_i, [_p, _p, _i64, _i, _i, _p, _p]),
+    'mmb_gauss_ll_stats': (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'mmb_word_ll_ids_workspace_bytes': (_sz, [_i, _i64, _i]),
     'mmb_word_ll_ids': (_i, [_p, _i, _i, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _i, _f, _p, _p,
                              _p, _sz, _p, _p]),

@@ -303,6 +303,90 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// ---- the same likelihood from per-utterance moments -------
+// The data of an utterance never changes between optimisation steps; only mu and sigma do.  With the
+// masked moments over time of each base feature,
+//     S0 = sum_t m,   mean = sum_t m x / S0,   M2 = sum_t m (x - mean)^2        (weights m = the float mask)
+// the masked squared distance to ANY mu is  sum_t m (x - mu)^2 = M2 + S0 (mean - mu)^2  (exact algebra, and
+// in this centred form free of the cancellation the raw-moment form S2 - 2 mu S1 + mu^2 S0 suffers), so
+//     lp_f = -0.5 log(2 pi sigma^2) S0 - (M2 + S0 (mean - mu)^2) / (2 sigma^2)
+//     d lp/d mu = S0 (mean - mu) / sigma^2,   d lp/d sigma = ((M2 + S0 (mean - mu)^2) / sigma^2 - S0) / sigma.
+// mmb_gauss_moments runs ONCE per dataset; every step then reads 3 floats per (utterance, feature)
+// instead of 2 T, and the (B, T, F) batch gathers of values and masks disappear from the step.
+//
+// stats layout: (N, 3, F) -- [S0 | mean | M2] rows of F floats per utterance.
+__global__ void __launch_bounds__(128)
+    gauss_moments_kernel(const float* __restrict__ val, const float* __restrict__ msk, int T, int F,
+                         float* __restrict__ stats) {
+  const int n = blockIdx.x;
+  const int f = blockIdx.y * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const float* x = val + (size_t)n * T * F + f;
+  const float* k = msk + (size_t)n * T * F + f;
+  float s0 = 0.f, s1 = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float mk = __ldg(k + (size_t)t * F);
+    s0 += mk;
+    s1 = fmaf(mk, __ldg(x + (size_t)t * F), s1);
+  }
+  const float mean = s0 != 0.f ? s1 / s0 : 0.f;
+  float m2 = 0.f;
+  for (int t = 0; t < T; ++t) {             // second pass over lines this thread just pulled into L1/L2
+    const float mk = __ldg(k + (size_t)t * F);
+    const float df = __ldg(x + (size_t)t * F) - mean;
+    m2 = fmaf(mk * df, df, m2);
+  }
+  float* o = stats + (size_t)n * 3 * F + f;
+  o[0] = s0;
+  o[F] = mean;
+  o[2 * F] = m2;
+}
+
+struct GaussStatArgs {
+  const float* st[kMaxMods][kMaxSegs];   // (B, 3, F) moments of the batch rows
+  int F[kMaxMods][kMaxSegs];
+  int n_seg[kMaxMods];
+  const float* mu[kMaxMods];
+  const float* sigma[kMaxMods];
+  float* dmu[kMaxMods];
+  float* dsigma[kMaxMods];
+  int D[kMaxMods];
+  int n_mod;
+};
+
+__global__ void __launch_bounds__(128)
+    gauss_ll_stats_kernel(const __grid_constant__ GaussStatArgs args, int B, float* __restrict__ lp,
+                          int* __restrict__ status) {
+  __shared__ float red[4];
+  const int b = blockIdx.x, m = blockIdx.y;
+  const int D = args.D[m];
+  float lp_acc = 0.f;
+  for (int f = threadIdx.x; f < D; f += blockDim.x) {
+    int seg = 0, fl = f;
+    while (seg + 1 < args.n_seg[m] && fl >= args.F[m][seg]) { fl -= args.F[m][seg]; ++seg; }
+    const int F = args.F[m][seg];
+    const float* st = args.st[m][seg] + (size_t)b * 3 * F + fl;
+    const float s0 = __ldg(st), mean = __ldg(st + F), m2 = __ldg(st + 2 * F);
+    const float mu = __ldg(args.mu[m] + (size_t)b * D + f);
+    const float sg = __ldg(args.sigma[m] + (size_t)b * D + f);
+    const float df = mean - mu;
+    const float q = fmaf(s0 * df, df, m2);
+    const float var = sg * sg;
+    const float inv_var = 1.f / var;
+    lp_acc += -0.5f * logf(6.283185307179586f * var) * s0 - 0.5f * q * inv_var;
+    if (args.dmu[m]) args.dmu[m][(size_t)b * D + f] = s0 * df * inv_var;
+    if (args.dsigma[m]) args.dsigma[m][(size_t)b * D + f] = (q * inv_var - s0) / sg;
+  }
+  lp_acc = warp_sum(lp_acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lp_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float s = red[0] + red[1] + red[2] + red[3];
+    lp[(size_t)m * B + b] = s;
+    if (!isfinite(s)) atomicOr(status, MMB_STATUS_NONFINITE);
+  }
+}
+
 // ---------------------------------------------------------------- word term (A8) -----
 __global__ void row_inv_norm_kernel(const float* __restrict__ X, int64_t n, int d, float* __restrict__ out) {
   // one warp per row: 1 / max(||x||, 1e-8)   (torch CosineSimilarity eps)
@@ -817,5 +901,46 @@ extern "C" int mmb_word_ll_ids(const float* latents, int B, int d, const float* 
   MMB_LAUNCH_CHECK("word_h_reduce");
   word_grad_finish_kernel<<<(B * d + 255) / 256, 256, 0, st>>>(G, latents, ie, aux, B, d, grad);
   MMB_LAUNCH_CHECK("word_grad_finish");
+  return MMB_OK;
+}
+
+extern "C" int mmb_gauss_moments(const float* val, const float* mask, int64_t N, int T, int F, float* stats,
+                                 mmb_stream_t stream) {
+  MMB_REQUIRE(N >= 0 && T > 0 && F > 0 && N < ((int64_t)1 << 31), "bad size");
+  if (N == 0) return MMB_OK;
+  MMB_REQUIRE(val && mask && stats, "null pointer");
+  gauss_moments_kernel<<<dim3((unsigned)N, (F + 127) / 128), 128, 0, as_stream(stream)>>>(val, mask, T, F, stats);
+  MMB_LAUNCH_CHECK("gauss_moments");
+  return MMB_OK;
+}
+
+extern "C" int mmb_gauss_ll_stats(int B, int n_mod, const int* n_seg, const float* const* seg_stats,
+                                  const int* seg_F, const float* const* mu, const float* const* sigma, float* lp,
+                                  float* const* dmu, float* const* dsigma, int* status, mmb_stream_t stream) {
+  MMB_REQUIRE(n_seg && seg_stats && seg_F && mu && sigma && lp && status, "null pointer");
+  MMB_REQUIRE(n_mod > 0 && n_mod <= kMaxMods, "1..8 modalities");
+  MMB_REQUIRE(B > 0, "bad size");
+  GaussStatArgs a = {};
+  int s = 0;
+  for (int m = 0; m < n_mod; ++m) {
+    MMB_REQUIRE(n_seg[m] > 0 && n_seg[m] <= kMaxSegs, "1..4 segments per modality");
+    a.n_seg[m] = n_seg[m];
+    int D = 0;
+    for (int g = 0; g < n_seg[m]; ++g, ++s) {
+      MMB_REQUIRE(seg_stats[s] && seg_F[s] > 0, "null segment");
+      a.st[m][g] = seg_stats[s];
+      a.F[m][g] = seg_F[s];
+      D += seg_F[s];
+    }
+    MMB_REQUIRE(mu[m] && sigma[m], "null mu/sigma");
+    a.mu[m] = mu[m];
+    a.sigma[m] = sigma[m];
+    a.dmu[m] = dmu ? dmu[m] : nullptr;
+    a.dsigma[m] = dsigma ? dsigma[m] : nullptr;
+    a.D[m] = D;
+  }
+  a.n_mod = n_mod;
+  gauss_ll_stats_kernel<<<dim3(B, n_mod), 128, 0, as_stream(stream)>>>(a, B, lp, status);
+  MMB_LAUNCH_CHECK("gauss_ll_stats");
   return MMB_OK;
 }

@@ -63,8 +63,39 @@ class TokenIds(object):
         return m[:, :, None].expand(*self.shape)
 
 
+class MomentStats(object):
+    """The masked moments over time of a (N, T, F) feature tensor, ``[S0 | mean | M2]`` as (N, 3, F): all the
+    Gaussian term ever needs of the data, computed once per dataset by
+    ``MomentStats.of(values, mask)``.  Usable wherever ``get_log_prob_matrix`` / ``get_normal_log_prob`` take a
+    values tensor or a ``CatSegments`` part (the matching mask entry is then ignored / may be None)."""
+
+    def __init__(self, stats):
+        self.stats = stats
+
+    @classmethod
+    def of(cls, values, mask):
+        if isinstance(values, TokenIds):
+            mask = values.mask() if mask is None else (mask[:, :, None].expand(*values.shape) if mask.dim() == 2 else mask)
+            values = values.materialize()
+        return cls(mmb_ops.gauss_moments(values, mask))
+
+    @property
+    def shape(self):
+        return (self.stats.shape[0], None, self.stats.shape[2])
+
+    def __len__(self):
+        return self.stats.shape[0]
+
+    def __getitem__(self, idx):
+        return MomentStats(self.stats[idx])
+
+
 def _segments(values, mask):
     v = values.parts if isinstance(values, CatSegments) else [values]
+    if all(isinstance(x, MomentStats) for x in v):
+        return [x.stats for x in v]
+    if any(isinstance(x, MomentStats) for x in v):
+        raise ValueError('a modality mixes MomentStats with raw tensors')
     k = mask.parts if isinstance(mask, CatSegments) else [mask]
     if len(v) == len(k):
         # a TokenIds part of a Gaussian modality is expanded for this batch only (B x T x d); its mask may
@@ -111,9 +142,19 @@ def get_normal_log_prob(mu, sigma, values, mask):
     """
     mu2 = mu.squeeze(1) if mu.dim() == 3 else mu
     sg2 = sigma.squeeze(1) if sigma.dim() == 3 else sigma
-    status = mmb_ops.new_status(values.device if values.is_cuda else mu.device)
-    lp = mmb_ops.GaussLLFunction.apply([_segments(values, mask)], status, mu2, sg2)
+    status = mmb_ops.new_status(mu.device)
+    lp = _gauss_apply([_segments(values, mask)], status, mu2, sg2)
     return lp[0]
+
+
+def _gauss_apply(segments, status, *mu_sigma):
+    """All modalities in one launch: from raw (values, mask) pairs, or from moments when every segment is one."""
+    is_stats = [not isinstance(seg[0], tuple) for seg in segments]
+    if all(is_stats):
+        return mmb_ops.GaussLLStatsFunction.apply(segments, status, *mu_sigma)
+    if any(is_stats):
+        raise ValueError('either all modalities come as MomentStats or none')
+    return mmb_ops.GaussLLFunction.apply(segments, status, *mu_sigma)
 
 
 def get_word_log_prob_angular(latents, weights, word_embeddings, data, mask, a):
@@ -199,7 +240,7 @@ def get_log_prob_matrix(args, latents, out, data, masks, word_log_prob_fn,
     flat = []
     for m in names:
         flat.extend([out[m]['mu'], out[m]['sigma']])
-    lp = mmb_ops.GaussLLFunction.apply([_segments(data[m], masks[m]) for m in names], status, *flat)
+    lp = _gauss_apply([_segments(data[m], masks.get(m)) for m in names], status, *flat)
     _exit_if_nonfinite(status, names)
 
     if verbose:

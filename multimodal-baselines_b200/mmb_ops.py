@@ -163,6 +163,55 @@ class GaussLLFunction(torch.autograd.Function):
         return tuple(grads)
 
 
+def gauss_moments(values, mask):
+    """(N, T, F) values + float mask -> (N, 3, F) masked moments over time [S0 | mean | M2]
+    (``mmb_gauss_moments``): computed once per dataset, see GaussLLStatsFunction."""
+    v, k = _f32(values), _f32(mask)
+    if v.dim() != 3 or v.shape != k.shape:
+        raise ValueError('values/mask must both be (n, seq_len, n_features)')
+    N, T, F = v.shape
+    stats = torch.empty((N, 3, F), dtype=torch.float32, device=v.device)
+    nv.check(lib.mmb_gauss_moments(nv.ptr(v), nv.ptr(k), N, T, F, nv.ptr(stats), nv.stream_ptr()))
+    return stats
+
+
+class GaussLLStatsFunction(torch.autograd.Function):
+    """GaussLLFunction fed with the per-utterance moments of the batch rows instead of the (B, T, F) values
+    and masks (``mmb_gauss_ll_stats``).  ``segments[m]`` = list of (B, 3, F) tensors."""
+
+    @staticmethod
+    def forward(ctx, segments, status, *mu_sigma):
+        mus = [_f32(t) for t in mu_sigma[0::2]]
+        sigmas = [_f32(t) for t in mu_sigma[1::2]]
+        n_mod = len(mus)
+        B = mus[0].shape[0]
+        stats, Fs, n_seg = [], [], []
+        for m in range(n_mod):
+            n_seg.append(len(segments[m]))
+            D = 0
+            for st in segments[m]:
+                st = _f32(st)
+                if st.dim() != 3 or st.shape[0] != B or st.shape[1] != 3:
+                    raise ValueError('moments must be (batch, 3, n_features)')
+                stats.append(st)
+                Fs.append(st.shape[2])
+                D += st.shape[2]
+            if mus[m].shape != (B, D) or sigmas[m].shape != (B, D):
+                raise RuntimeError('The size of mu/sigma %s must match the data (%d, %d)'
+                                   % (tuple(mus[m].shape), B, D))
+        lp = torch.empty((n_mod, B), dtype=torch.float32, device=mus[0].device)
+        dmu = [torch.empty_like(t) for t in mus]
+        dsg = [torch.empty_like(t) for t in sigmas]
+        nv.check(lib.mmb_gauss_ll_stats(B, n_mod, _int_array(n_seg), _ptr_array(stats), _int_array(Fs),
+                                        _ptr_array(mus), _ptr_array(sigmas), nv.ptr(lp), _ptr_array(dmu),
+                                        _ptr_array(dsg), nv.ptr(status), nv.stream_ptr()))
+        ctx.save_for_backward(*dmu, *dsg)
+        ctx.n_mod = n_mod
+        return lp
+
+    backward = staticmethod(GaussLLFunction.backward)
+
+
 class WordLLFunction(torch.autograd.Function):
     """Angular word log-probability (reference losses.py:68-95) with its gradient w.r.t. the
     latents; the word table, token vectors, weights and mask are constants of the step."""

@@ -26,7 +26,7 @@ import torch.nn as nn
 import torch.optim as optim
 from torch.utils.data import DataLoader
 
-from losses import CatSegments, TokenIds, get_log_prob_matrix, get_word_log_prob_angular, get_word_log_prob_dot_prod  # noqa: F401
+from losses import CatSegments, MomentStats, TokenIds, get_log_prob_matrix, get_word_log_prob_angular, get_word_log_prob_dot_prod  # noqa: F401
 from losses import get_word_log_prob_angular2
 from models import AudioVisualGeneratorConcat, AudioVisualGenerator, AudioVisualGeneratorMultimodal  # noqa: F401
 from sentiment_model import SentimentData, SentimentModel, train_sentiment_for_latents
@@ -57,14 +57,17 @@ def _batch_dicts(args, x, table=None):
     """The per-step ``batch_data`` / ``batch_masks`` of reference simplesif.py:72-124, with the
     concatenated modalities expressed as CatSegments instead of materialised torch.cat.  A batch of an
     id-based dataset (``MMDataIds``: int64 ids in the text slot) is wrapped as ``TokenIds(ids, table)``."""
+    text_moments = None
     if args['dataset'] == 'mosi':
+        if len(x) == 9:                    # _with_moments: the text's moments ride behind the tuple
+            x, text_moments = x[:8], x[8]
         j, text, aud, vis, text_m, aud_m, vis_m, text_w = x
     else:
         j, text, aud, vis, text_m, aud_m, vis_m, text_w, text_gauss, text_gauss_m = x
     if torch.is_tensor(text) and text.dtype == torch.int64:
         text = TokenIds(text, table)
     if args['dataset'] == 'mosi':
-        text_gauss, text_gauss_m = text, text_m
+        text_gauss, text_gauss_m = (text, text_m) if text_moments is None else (text_moments, None)
     batch_data = {'text': text, 'audio': aud, 'visual': vis, 'text_weights': text_w}
     batch_masks = {'text': text_m, 'audio': aud_m, 'visual': vis_m}
     if not args['unimodal']:
@@ -81,6 +84,49 @@ def _batch_dicts(args, x, table=None):
             'textaudiovisual': CatSegments([text_gauss_m, aud_m, vis_m]),
         })
     return j, batch_data, batch_masks
+
+
+def _dataset_moments(args, dataset):
+    """The per-utterance moments of every tensor the Gaussian terms read, computed
+    once per dataset and cached on it: the data of an utterance is the same at every step of every epoch, so
+    the loops hand ``get_log_prob_matrix`` 3 numbers per (utterance, feature) instead of the (B, T, F) values
+    and masks.  ``args['gauss_moments'] = 0`` (or MMB_GAUSS_MOMENTS=0) keeps the raw tensors."""
+    flag = args.get('gauss_moments', os.environ.get('MMB_GAUSS_MOMENTS', '1'))
+    if str(flag) in ('0', 'False', 'false', '') or not hasattr(dataset, 'audio_mask'):
+        return None
+    if not dataset.audio.is_cuda:
+        return None
+    cached = getattr(dataset, '_gauss_moments', None)
+    key = (args['dataset'], bool(args['unimodal']))
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    mom = {'audio': MomentStats.of(dataset.audio, dataset.audio_mask),
+           'visual': MomentStats.of(dataset.visual, dataset.visual_mask)}
+    if not args['unimodal']:
+        if args['dataset'] != 'mosi':
+            mom['text_gauss'] = MomentStats.of(dataset.text_aligned, dataset.text_aligned_mask)
+        elif hasattr(dataset, 'text_ids'):
+            mom['text_gauss'] = MomentStats.of(TokenIds(dataset.text_ids, dataset.table), dataset.text_mask)
+        else:
+            mom['text_gauss'] = MomentStats.of(dataset.text, dataset.text_mask)
+    dataset._gauss_moments = (key, mom)
+    return mom
+
+
+def _with_moments(args, x, moments):
+    """A batch tuple (reference utils.py:231-233 / 248-251) with the Gaussian inputs replaced by the moments
+    of its rows; the word term's inputs (text, text mask, weights) are untouched."""
+    if moments is None:
+        return x
+    x = list(x)
+    j = x[0]
+    x[2], x[3], x[5], x[6] = moments['audio'][j], moments['visual'][j], None, None
+    if 'text_gauss' in moments:
+        if args['dataset'] == 'mosi':
+            x.append(moments['text_gauss'][j])     # consumed by _batch_dicts as the Gaussian view of the text
+        else:
+            x[8], x[9] = moments['text_gauss'][j], None
+    return tuple(x)
 
 
 def _make_optimizer(args, params, lr):
@@ -120,10 +166,27 @@ class GraphedStep(object):
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.graphs = {}
         self.mmb_ops = mmb_ops
+        self.moments = _dataset_moments(args, dataset)
 
     def _gather(self, j):
         """``dataset[j]`` (reference utils.py:231-233 / 248-251) as one multi-tensor gather launch."""
         ds = self.dataset
+        mom = self.moments
+        if mom is not None:
+            # word-term inputs + the moments of the Gaussian inputs: one multi-tensor launch of small rows
+            keys = ['audio', 'visual'] + (['text_gauss'] if 'text_gauss' in mom else [])
+            srcs = ([] if hasattr(ds, 'text_ids') else [ds.text]) + [ds.text_mask, ds.text_weights] + \
+                [mom[k].stats for k in keys]
+            got = list(self.mmb_ops.gather_multi(srcs, j))
+            text = ds.text_ids[j] if hasattr(ds, 'text_ids') else got.pop(0)
+            text_m, text_w = got[0], got[1]
+            st = {k: MomentStats(t) for k, t in zip(keys, got[2:])}
+            x = (j, text, st['audio'], st['visual'], text_m, None, None, text_w)
+            if 'text_gauss' in st:
+                x = x + ((st['text_gauss'],) if self.args['dataset'] == 'mosi' else (st['text_gauss'], None))
+            elif self.args['dataset'] != 'mosi':
+                x = x + (None, None)
+            return x
         names = ['text', 'audio', 'visual', 'text_mask', 'audio_mask', 'visual_mask', 'text_weights']
         if hasattr(ds, 'text_aligned'):
             names += ['text_aligned', 'text_aligned_mask']
@@ -268,6 +331,7 @@ def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epoc
         optimizer = _make_optimizer(args, grad_params, lr)
     stepper = GraphedStep(args, gen_model, embeddings, dataloader.dataset, optimizer, word_prob_fn,
                           device) if graphed else None
+    moments = None if graphed else _dataset_moments(args, dataloader.dataset)
 
     valid_niter = 10
     start_time = time.time()
@@ -283,7 +347,8 @@ def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epoc
             stepper.check()
         else:
             for x in dataloader:
-                j, batch_data, batch_masks = _batch_dicts(args, x, getattr(dataloader.dataset, 'table', None))
+                j, batch_data, batch_masks = _batch_dicts(args, _with_moments(args, x, moments),
+                                                          getattr(dataloader.dataset, 'table', None))
                 iters += 1
                 optimizer.zero_grad()
                 out = gen_model(embeddings[j])
@@ -364,6 +429,7 @@ def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, 
 
     stepper = GraphedStep(args, gen_model, train_embed, dataloader.dataset, optimizer, word_prob_fn, device,
                           extra_loss=mixed_loss, extra_modules=[senti_model]) if graphed else None
+    moments = None if graphed else _dataset_moments(args, dataloader.dataset)
     train_losses, all_valid_losses = [], []
     start_time = time.time()
     n_epochs = n_epochs if n_epochs is not None else args['n_epochs']
@@ -377,7 +443,8 @@ def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, 
             stepper.check()
         else:
             for x in dataloader:
-                j, batch_data, batch_masks = _batch_dicts(args, x, getattr(dataloader.dataset, 'table', None))
+                j, batch_data, batch_masks = _batch_dicts(args, _with_moments(args, x, moments),
+                                                          getattr(dataloader.dataset, 'table', None))
                 iters += 1
                 optimizer.zero_grad()
                 out = gen_model(train_embed[j])

@@ -180,6 +180,48 @@ def test_word_term_ids_long_transcripts(mods):
     assert int(st.item()) & 1
 
 
+@pytest.mark.parametrize('tag', list(cases.MMB_CASES))
+def test_gaussian_terms_from_moments(mods, golden_dir, tag):
+    """the Gaussian terms fed with the per-utterance moments [S0 | mean | M2]
+    (losses.MomentStats, computed once per dataset) instead of the (B, T, F) values and masks -- the whole
+    step against the reference golden (values and every gradient), and against the direct kernel."""
+    torch, losses, models = mods
+    g = np.load(os.path.join(golden_dir, 'mmb_%s.npz' % tag))
+    cfg, c, t, model, data, masks = build(torch, models, losses, tag, True)
+    M = losses.MomentStats.of
+    aud, vis, txt = M(t['aud'], t['aud_m']), M(t['vis'], t['vis_m']), M(t['text'], t['text_m'])
+    assert tuple(aud.stats.shape) == (t['aud'].shape[0], 3, t['aud'].shape[2])
+    d2 = {'text': t['text'], 'text_weights': t['text_w'], 'audio': aud, 'visual': vis}
+    m2 = {'text': t['text_m']}
+    if not cfg['unimodal']:
+        C = losses.CatSegments
+        d2.update(audiovisual=C([aud, vis]), textaudio=C([txt, aud]), textvisual=C([txt, vis]),
+                  textaudiovisual=C([txt, aud, vis]))
+    word_fn = lambda l, w, s_, m: losses.get_word_log_prob_angular2(l, t['We'], w, s_, m, 1e-3)
+    lat = t['latents'].clone().requires_grad_(True)
+    out = model(lat)
+    total = losses.get_log_prob_matrix(dict(cfg['args']), lat, out, d2, m2, word_fn)
+    close(total.detach().cpu(), g['total'], VAL_RTOL, 'total')
+    (-total).mean().backward()
+    close(lat.grad.cpu(), g['grad_latents'], GRAD_RTOL, 'grad_latents')
+    for mod in out:
+        for nm in ('mu', 'log_sigma'):
+            gW = model.embed2out[mod][nm].weight.grad.cpu().numpy()
+            want = g['gW_%s_%s' % (nm, mod)]
+            close(gW if gW.size <= 4096 else gW[:8], want, GRAD_RTOL, 'gW %s %s' % (nm, mod))
+    # per modality against the direct kernel, incl. a fully masked feature (S0 = 0) and T = 1
+    for mod, dd in out.items():
+        lp_m = losses.get_normal_log_prob(dd['mu'].detach().unsqueeze(1), dd['sigma'].detach().unsqueeze(1), d2[mod], None)
+        close(lp_m.cpu(), g['lp_' + mod], VAL_RTOL, 'lp ' + mod)
+    x = torch.randn(5, 1, 7, device='cuda')
+    k = (torch.rand(5, 1, 7, device='cuda') > 0.3).float()
+    k[:, :, 2] = 0
+    mu, sg = torch.randn(5, 7, device='cuda'), torch.rand(5, 7, device='cuda') + 0.5
+    a = losses.get_normal_log_prob(mu, sg, x, k)
+    b = losses.get_normal_log_prob(mu, sg, M(x, k), None)
+    close(b.cpu(), a.cpu(), 1e-5, 'T=1 / empty feature')
+
+
 def test_frozen_heads_and_latent_only_grads(mods):
     """optimize_latents(train=False) / freeze_weights: only the latents receive gradients."""
     torch, losses, models = mods
