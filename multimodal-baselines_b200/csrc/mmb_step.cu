@@ -22,37 +22,49 @@ constexpr int kMaxSegs = 4;
 // Operand tiles go through shared memory transposed to [k][m] / [k][n] so that the inner
 // product reads two float4 per k.  Small-matrix helper: the problems here are <= 512 x 3016 x 425.
 // --------------------------------------------------------------------------------------
-constexpr int kTM = 64, kTN = 64, kTK = 16;
+constexpr int kTM = 64, kTN = 64, kTK = 32;
+constexpr int kStageElems = kTM * kTK / 256;   // operand elements each thread stages per k-tile
 
 struct TileSmem {
   float a[kTK][kTM + 4];
   float b[kTK][kTN + 4];
 };
 
+// The problems are tiny (one to a few CTAs per SM, K of a few hundred), so a k-tile's global loads are pure
+// exposed latency unless they are in flight while the previous tile is multiplied: the next tile is
+// prefetched into registers right after the barrier that publishes the current one (software pipeline,
+// one stage).  The k order of every output element is unchanged (0 .. K-1), so results are bit-identical
+// to the unpipelined loop.
 __device__ __forceinline__ void tile_gemm_accum(TileSmem& sm, float (&acc)[4][4], const float* __restrict__ A,
                                                 int64_t a_rs, int64_t a_cs, const float* __restrict__ Bm,
                                                 int64_t b_rs, int64_t b_cs, int m0, int n0, int M, int N, int K) {
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  for (int k0 = 0; k0 < K; k0 += kTK) {
-    // stage: 64 x 16 elements of each operand, 4 per thread
+  // make the fastest-varying thread index follow the smaller stride of each operand
+  const bool a_kfast = a_cs <= a_rs, b_kfast = b_rs <= b_cs;
+  float ra[kStageElems], rb[kStageElems];
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int idx = tid + 256 * e;          // 0..1023
-      {
-        // A: make the fastest-varying thread index follow the smaller stride
-        const int mm = (a_cs <= a_rs) ? idx / kTK : idx % kTM;
-        const int kk = (a_cs <= a_rs) ? idx % kTK : idx / kTM;
-        const int m = m0 + mm, k = k0 + kk;
-        sm.a[kk][mm] = (m < M && k < K) ? __ldg(A + m * a_rs + k * a_cs) : 0.f;
-      }
-      {
-        const int nn = (b_rs <= b_cs) ? idx / kTK : idx % kTN;
-        const int kk = (b_rs <= b_cs) ? idx % kTK : idx / kTN;
-        const int n = n0 + nn, k = k0 + kk;
-        sm.b[kk][nn] = (n < N && k < K) ? __ldg(Bm + k * b_rs + n * b_cs) : 0.f;
-      }
+    for (int e = 0; e < kStageElems; ++e) {
+      const int idx = tid + 256 * e;
+      const int mm = a_kfast ? idx / kTK : idx % kTM, ka = a_kfast ? idx % kTK : idx / kTM;
+      const int nn = b_kfast ? idx / kTK : idx % kTN, kb = b_kfast ? idx % kTK : idx / kTN;
+      const int m = m0 + mm, n = n0 + nn;
+      ra[e] = (m < M && k0 + ka < K) ? __ldg(A + m * a_rs + (k0 + ka) * a_cs) : 0.f;
+      rb[e] = (n < N && k0 + kb < K) ? __ldg(Bm + (k0 + kb) * b_rs + n * b_cs) : 0.f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += kTK) {
+#pragma unroll
+    for (int e = 0; e < kStageElems; ++e) {
+      const int idx = tid + 256 * e;
+      const int mm = a_kfast ? idx / kTK : idx % kTM, ka = a_kfast ? idx % kTK : idx / kTM;
+      const int nn = b_kfast ? idx / kTK : idx % kTN, kb = b_kfast ? idx % kTK : idx / kTN;
+      sm.a[ka][mm] = ra[e];
+      sm.b[kb][nn] = rb[e];
     }
     __syncthreads();
+    if (k0 + kTK < K) fetch(k0 + kTK);
 #pragma unroll
     for (int kk = 0; kk < kTK; ++kk) {
       const float4 a = *(const float4*)&sm.a[kk][ty * 4];
