@@ -37,6 +37,7 @@ for _p in (ROOT, PKG):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+OUT = sys.stdout
 METRIC = 'utterances/sec (SIF embed + PC removal)'
 UNIT = 'utterances/s'
 N_UTT = int(os.environ.get('MMB_BENCH_N', 10_000_000))
@@ -195,7 +196,7 @@ def run_reference_arm(args):
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
-    }), flush=True)
+    }), file=OUT, flush=True)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -265,6 +266,13 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    # stdout carries exactly ONE JSON line: keep the real stdout for it and point fd 1 at stderr, so that
+    # whatever else writes to fd 1 (NCCL's version banner at NCCL_DEBUG >= VERSION, library prints, the
+    # reference helpers' progress lines) cannot land in front of it
+    global OUT
+    sys.stdout.flush()
+    OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.impl == 'reference':
         run_reference_arm(args)
         return
@@ -450,7 +458,7 @@ def main():
                              % (n_local * L_TOK * 8 / 1e9, n_local * DIM * 4 / 1e9)},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': LAUNCHES_PER_STEP * args.steps,
             'roofline': roofline, 'cpu_baseline': cpu,
-        }), flush=True)
+        }), file=OUT, flush=True)
     if world > 1:
         mdist.close_default_comms()
         dist.destroy_process_group()
