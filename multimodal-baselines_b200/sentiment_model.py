@@ -110,6 +110,7 @@ class _GraphedSentimentStep(object):
     def __init__(self, model, latents, labels, optimizer):
         self.model, self.latents, self.labels, self.optimizer = model, latents, labels, optimizer
         self.graphs = {}
+        self.epoch_graphs = {}
 
     def _step(self, j):
         loss = _l1(self.model, self.latents, self.labels, j)[0].mean()
@@ -144,6 +145,40 @@ class _GraphedSentimentStep(object):
         graph.replay()
         return static_loss
 
+    def run_epoch(self, flat, sizes):
+        """All SGD steps of one epoch as ONE graph replay (the batches are static slices of one index
+        buffer); returns the (device) sum of the per-step losses."""
+        key = tuple(int(n) for n in sizes)
+        if key not in self.epoch_graphs:
+            dev = self.latents.device
+            static_flat = torch.zeros(int(sum(key)), dtype=torch.int64, device=dev)
+            params = [p for g in self.optimizer.param_groups for p in g['params']]
+            saved = [p.detach().clone() for p in params]
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for n in sorted(set(key)) * 2:
+                    self.optimizer.zero_grad(set_to_none=True)
+                    self._step(static_flat[:n])
+            torch.cuda.current_stream(dev).wait_stream(side)
+            with torch.no_grad():
+                for p, s_ in zip(params, saved):
+                    p.copy_(s_)
+            graph = torch.cuda.CUDAGraph()
+            self.optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                total = torch.zeros((), device=dev)
+                off = 0
+                for n in key:
+                    self.optimizer.zero_grad(set_to_none=True)
+                    total = total + self._step(static_flat[off:off + n])
+                    off += n
+            self.epoch_graphs[key] = (graph, static_flat, total)
+        graph, static_flat, total = self.epoch_graphs[key]
+        static_flat.copy_(flat)
+        graph.replay()
+        return total
+
 
 def train_sentiment(args, model, train_data, train_latents, valid_data, valid_latents, model_loader=None,
                     valid_niter=10, verbose=False, model_save_path=None):
@@ -169,7 +204,14 @@ def train_sentiment(args, model, train_data, train_latents, valid_data, valid_la
     for i in range(n_epochs):
         epoch_loss = torch.zeros((), device=device)
         n_batches = 0
-        for j in _index_batches(train_data, device):
+        if graphed and str(args.get('cuda_graph')) != 'step':
+            torch.empty((), dtype=torch.int64).random_(generator=train_data.generator)    # as _index_batches
+            batches = list(train_data.batch_sampler)
+            n_batches = len(batches)
+            if n_batches:
+                flat = torch.tensor([k for b in batches for k in b], dtype=torch.int64).to(device, non_blocking=True)
+                epoch_loss = stepper.run_epoch(flat, [len(b) for b in batches])
+        for j in (() if graphed and str(args.get('cuda_graph')) != 'step' else _index_batches(train_data, device)):
             n_batches += 1
             if graphed:
                 epoch_loss += stepper(j)

@@ -165,6 +165,7 @@ class GraphedStep(object):
         self.dataset, self.optimizer, self.word_prob_fn, self.device = dataset, optimizer, word_prob_fn, device
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.graphs = {}
+        self.epoch_graphs = {}
         self.mmb_ops = mmb_ops
         self.moments = _dataset_moments(args, dataset)
 
@@ -277,6 +278,59 @@ class GraphedStep(object):
         finally:
             self.mmb_ops.set_status_sink(prev)
 
+    def _capture_epoch(self, sizes):
+        """Capture a WHOLE epoch -- one step per batch, the batches being static slices of one index buffer
+        -- as a single graph: one replay (and one small index upload) per epoch instead of one per step."""
+        n_total = int(sum(sizes))
+        static_flat = torch.zeros(n_total, dtype=torch.int64, device=self.device)
+        params, saved, bufs = self._snapshot()
+        had_state = len(self.optimizer.state) > 0
+        state_saved = None
+        if had_state:
+            state_saved = [{k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                           for st in self.optimizer.state.values()]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for n in sorted(set(sizes)) * 2:          # warm every batch size (allocator, lazy inits)
+                self.optimizer.zero_grad(set_to_none=True)
+                self._step(static_flat[:n])
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self._restore(params, saved, bufs)
+        self.status.zero_()
+        if had_state:
+            with torch.no_grad():
+                for st, old in zip(self.optimizer.state.values(), state_saved):
+                    for k, v in old.items():
+                        if torch.is_tensor(v):
+                            st[k].copy_(v)
+        graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            total = torch.zeros((), device=self.device)
+            off = 0
+            for n in sizes:
+                self.optimizer.zero_grad(set_to_none=True)
+                total = total + self._step(static_flat[off:off + n])
+                off += n
+        return graph, static_flat, total
+
+    def run_epoch(self, flat, sizes):
+        """All steps of one epoch: ``flat`` = the epoch's row indices in visiting order (int64 CUDA tensor),
+        ``sizes`` = the batch sizes.  Returns the (device) sum of the per-step losses, as the reference's
+        ``epoch_loss`` accumulates them (simplesif.py:139)."""
+        prev = self.mmb_ops.set_status_sink(self.status)
+        try:
+            key = tuple(int(n) for n in sizes)
+            if key not in self.epoch_graphs:
+                self.epoch_graphs[key] = self._capture_epoch(key)
+            graph, static_flat, total = self.epoch_graphs[key]
+            static_flat.copy_(flat)
+            graph.replay()
+            return total
+        finally:
+            self.mmb_ops.set_status_sink(prev)
+
     def check(self):
         from losses import check_status_sink
         check_status_sink(self.status, list(self.gen_model.embed2out.keys()))
@@ -296,6 +350,19 @@ def _epoch_index_batches(dataloader, device):
     for b in batches:
         yield flat[off:off + len(b)]
         off += len(b)
+
+
+def _epoch_indices(dataloader, device):
+    """``_epoch_index_batches`` as one flat index tensor + the batch sizes (same draws from the generator)."""
+    torch.empty((), dtype=torch.int64).random_(generator=dataloader.generator)
+    batches = list(dataloader.batch_sampler)
+    flat = torch.tensor([i for b in batches for i in b], dtype=torch.int64).to(device, non_blocking=True)
+    return flat, [len(b) for b in batches]
+
+
+def _graph_epochs(args):
+    """Whole-epoch graphs unless ``args['cuda_graph'] == 'step'`` (one graph per step)."""
+    return str(args.get('cuda_graph', os.environ.get('MMB_CUDA_GRAPH', '0'))) != 'step'
 
 
 def _use_cuda_graph(args, gen_model, device):
@@ -340,7 +407,13 @@ def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epoc
     for i in range(n_epochs):
         epoch_loss = torch.zeros((), device=device)
         iters = 0
-        if graphed:
+        if graphed and _graph_epochs(args):
+            flat, sizes = _epoch_indices(dataloader, device)
+            iters = len(sizes)
+            if iters:
+                epoch_loss = stepper.run_epoch(flat, sizes)
+            stepper.check()
+        elif graphed:
             for j in _epoch_index_batches(dataloader, device):
                 iters += 1
                 epoch_loss += stepper(j)
@@ -436,7 +509,13 @@ def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, 
     for i in range(n_epochs):
         epoch_loss = torch.zeros((), device=device)
         iters = 0
-        if graphed:
+        if graphed and _graph_epochs(args):
+            flat, sizes = _epoch_indices(dataloader, device)
+            iters = len(sizes)
+            if iters:
+                epoch_loss = stepper.run_epoch(flat, sizes)
+            stepper.check()
+        elif graphed:
             for j in _epoch_index_batches(dataloader, device):
                 iters += 1
                 epoch_loss += stepper(j)

@@ -327,7 +327,7 @@ def test_cuda_graph_step_matches_eager_loop(mods, golden_dir, tag, shuffle):
         We_t = torch.tensor(c['We'], device=dev)
         word_fn = simplesif.make_word_log_prob_fn({'word_sim_metric': 'angular'}, None, We_t)
         args = dict(cfg['args'])
-        args['cuda_graph'] = 1 if graph else 0
+        args['cuda_graph'] = graph if isinstance(graph, str) else (1 if graph else 0)
         emb, (ls, _) = simplesif.optimize_latents(args, cfg['train'], model, c['latents'], loader, cfg['epochs'],
                                                   cfg['lr'], word_fn, dev, verbose=False)
         return emb.cpu().numpy(), np.array(ls), model.embed2out['audio']['mu'].weight.detach().cpu().numpy()
@@ -337,6 +337,9 @@ def test_cuda_graph_step_matches_eager_loop(mods, golden_dir, tag, shuffle):
         close(ls_g, g[tag + '_losses'], 2e-4, 'losses')
         close(emb_g, g[tag + '_emb'], 1e-3, 'latents')
         close(W_g, g[tag + '_Wmu_audio'], 1e-3, 'W')
+    emb_s, ls_s, W_s = run('step')          # one graph per step instead of one per epoch: the same kernels
+    close(ls_g, ls_s, 1e-6, 'losses, epoch graph vs step graphs')
+    close(emb_g, emb_s, 1e-6, 'latents, epoch graph vs step graphs')
     emb_e, ls_e, W_e = run(False)
     close(ls_g, ls_e, 1e-5, 'losses vs eager')
     close(emb_g, emb_e, 1e-5, 'latents vs eager')
