@@ -183,6 +183,7 @@ def main(argv=None):
     ap.add_argument('--limit', type=int, default=0, help='only the first K configs of the grid (0 = all 512)')
     ap.add_argument('--epochs-scale', type=float, default=1.0, help='scale n_epochs / n_sentiment_epochs (smoke runs)')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--only', type=int, nargs='*', default=None, help='run just these config numbers')
     ap.add_argument('--out', default='')
     a = ap.parse_args(argv)
     import torch.distributed as dist
@@ -199,6 +200,8 @@ def main(argv=None):
     grid = make_grid()
     if a.limit:
         grid = grid[:a.limit]
+    if a.only:
+        grid = [c for c in grid if c['config_num'] in set(a.only)]
     mine = grid[rank::world]
     We, weights, splits = synthetic_mosi()
     devnull = open(os.devnull, 'w')
