@@ -81,6 +81,14 @@ def _index_batches(loader, device):
         off += len(b)
 
 
+def _epoch_indices(loader, device):
+    """``_index_batches`` as one flat index tensor + the batch sizes (same draws from the generator)."""
+    torch.empty((), dtype=torch.int64).random_(generator=loader.generator)
+    batches = list(loader.batch_sampler)
+    flat = torch.tensor([i for b in batches for i in b], dtype=torch.int64).to(device, non_blocking=True)
+    return flat, [len(b) for b in batches]
+
+
 def _l1(model, latents, labels, j):
     senti = labels[j]
     return (model(latents[j]).reshape(senti.shape) - senti).abs(), senti
@@ -196,6 +204,7 @@ def train_sentiment(args, model, train_data, train_latents, valid_data, valid_la
     optimizer = optim.SGD(model.parameters(), lr=lr)
     graphed = str(args.get('cuda_graph', 0)) not in ('0', 'False', 'false', '') and train_latents.is_cuda
     stepper = _GraphedSentimentStep(model, train_latents, labels, optimizer) if graphed else None
+    graph_epochs = graphed and str(args.get('cuda_graph')) != 'step'    # one graph per epoch, else one per step
     ckpt_file = os.path.join(model_save_path, 'senti.bin') if model_save_path is not None else None
 
     train_losses, valid_losses = [], []
@@ -204,23 +213,22 @@ def train_sentiment(args, model, train_data, train_latents, valid_data, valid_la
     for i in range(n_epochs):
         epoch_loss = torch.zeros((), device=device)
         n_batches = 0
-        if graphed and str(args.get('cuda_graph')) != 'step':
-            torch.empty((), dtype=torch.int64).random_(generator=train_data.generator)    # as _index_batches
-            batches = list(train_data.batch_sampler)
-            n_batches = len(batches)
+        if graph_epochs:
+            flat, sizes = _epoch_indices(train_data, device)
+            n_batches = len(sizes)
             if n_batches:
-                flat = torch.tensor([k for b in batches for k in b], dtype=torch.int64).to(device, non_blocking=True)
-                epoch_loss = stepper.run_epoch(flat, [len(b) for b in batches])
-        for j in (() if graphed and str(args.get('cuda_graph')) != 'step' else _index_batches(train_data, device)):
-            n_batches += 1
-            if graphed:
-                epoch_loss += stepper(j)
-            else:
-                model.zero_grad()
-                loss = _l1(model, train_latents, labels, j)[0].mean()
-                loss.backward()
-                optimizer.step()
-                epoch_loss += loss.detach()
+                epoch_loss = stepper.run_epoch(flat, sizes)
+        else:
+            for j in _index_batches(train_data, device):
+                n_batches += 1
+                if graphed:
+                    epoch_loss += stepper(j)
+                else:
+                    model.zero_grad()
+                    loss = _l1(model, train_latents, labels, j)[0].mean()
+                    loss.backward()
+                    optimizer.step()
+                    epoch_loss += loss.detach()
         train_losses.append(float(epoch_loss) / max(n_batches, 1))
         if i % valid_niter == 0:
             batches = 0

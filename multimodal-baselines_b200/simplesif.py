@@ -144,6 +144,26 @@ def _warn_tiny_sigma(out):
         print({m: float(d['sigma'].min()) for m, d in out.items()}, "boo!")
 
 
+class _RowGather(torch.autograd.Function):
+    """``embeddings[j]`` with a leaner backward for the captured step: the dense gradient the optimizers need
+    (reference simplesif.py:54-61 steps the whole (N, d) latent tensor) is a zero fill plus ``index_add_``
+    -- two launches instead of the sort-based ``index_put_(accumulate=True)`` chain of advanced indexing
+    (six).  Same values: a DataLoader batch never repeats a row, and repeated rows would still be summed."""
+
+    @staticmethod
+    def forward(ctx, table, j):
+        ctx.save_for_backward(j)
+        ctx.n = table.shape[0]
+        return table.index_select(0, j)
+
+    @staticmethod
+    def backward(ctx, g):
+        (j,) = ctx.saved_tensors
+        grad = torch.zeros((ctx.n,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+        grad.index_add_(0, j, g)
+        return grad, None
+
+
 class GraphedStep(object):
     """One latent-optimisation step -- gather the batch, generator heads, word + Gaussian
     log-likelihoods, backward, optimizer step -- captured ONCE as a CUDA graph and replayed per
@@ -199,7 +219,7 @@ class GraphedStep(object):
     def _step(self, j):
         x = self._gather(j)                       # batched gather of the device-resident tensors
         _, batch_data, batch_masks = _batch_dicts(self.args, x, getattr(self.dataset, 'table', None))
-        e = self.embeddings[j]
+        e = _RowGather.apply(self.embeddings, j)
         out = self.gen_model(e)
         log_prob = -get_log_prob_matrix(self.args, e, out, batch_data, batch_masks, self.word_prob_fn,
                                         device=self.device, verbose=False)
