@@ -141,3 +141,36 @@ def test_sentiment_regressor_matches_reference(golden_dir, tag, tmp_path, capsys
     np.testing.assert_allclose(np.asarray(before['mae'], dtype=np.float64), g[tag + '_before_mae'], atol=2e-6)
     for name in ('test_results_after.json', 'senti_train_loss.txt', 'senti_valid_loss.txt', 'senti.bin'):
         assert (tmp_path / name).exists(), name
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside the GPU arm): stdout is exactly one
+    JSON line with the contract's keys, whatever the libraries print (fd 1 is pointed at stderr)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MMB_REF_SAMPLE='300', MMB_BENCH_V='5000')
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                        '--warmup', '0'], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    line = json.loads(lines[0])
+    assert line['impl'] == 'reference' and line['unit'] == 'utterances/s' and line['higher_is_better'] is True
+    assert line['value'] > 0 and line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e'] == {'value': line['value'], 'unit': line['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert line['gpu_launches'] == 0 and 'workload' in line['config']
+
+
+def test_bench_gpu_arm_refuses_to_run_without_cuda():
+    """No CPU fallback: without a CUDA device the GPU arm exits non-zero and prints no result line."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA device present')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0
+    assert not [l for l in r.stdout.splitlines() if l.strip().startswith('{')]
