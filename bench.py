@@ -413,7 +413,7 @@ def main():
     embed_s = stage_ms['embed'] * 1e-3
     traffic = load_traffic(n_local) if IDS_KIND == 'zipf' else None
     achieved = n_local * EMBED_BYTES_PER_UTT / embed_s / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'sif_embed_warp_kernel<3,false>', 'achieved': achieved, 'peak': peak,
+    roofline = {'bound': 'hbm', 'kernel': 'sif_embed_warp_prefetch_kernel<3,2,4>', 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                 # what HBM itself carried (ncu DRAM bytes of the committed capture / this run's launch time):
                 # the gap to `achieved` is rows served by L1/L2 (Zipf head + merged pad runs)

@@ -111,19 +111,22 @@ template <> struct RowOff<true> { typedef unsigned long long type; };
 // by one (pad id 0 is an ordinary row with weight 1.0 in the POM weights), and natural text
 // repeats its most frequent words (Zipf: ~18 % of the non-pad tokens of a 32-token chunk).
 // The divisor still counts every token's own weight.
-template <int NCH, bool EXPLICIT_W, int UNROLL, bool WIDE>
+// PRE: the lane's id was loaded one chunk ago (`pre_id`, software prefetch by the caller) -- the ids are
+// the only operand of this kernel that streams from DRAM, and the weight gather and every row address
+// depend on them.
+template <int NCH, bool EXPLICIT_W, int UNROLL, bool WIDE, bool PRE = false>
 __device__ __forceinline__ int accumulate_chunk(RowAcc<NCH>& acc, const char* __restrict__ lane_base,
                                                 int V, unsigned row_bytes, bool tail,
                                                 const float* __restrict__ wsrc,
                                                 const int64_t* __restrict__ row_ids,
                                                 const float* __restrict__ row_w, int64_t base,
-                                                int64_t L, int lane, bool& bad) {
+                                                int64_t L, int lane, bool& bad, int64_t pre_id = 0) {
   typedef typename RowOff<WIDE>::type off_t;
   const int64_t t = base + lane;
   float w = 0.f;
   int row = -1;                       // -1: no token in this lane (past the end / bad index)
   if (t < L) {
-    const int64_t id = __ldcs(row_ids + t);
+    const int64_t id = PRE ? pre_id : __ldcs(row_ids + t);
     const int64_t r = id < 0 ? id + V : id;
     if (r >= 0 && r < V) {
       row = (int)r;
@@ -222,6 +225,41 @@ __device__ __forceinline__ void store_row(float4* __restrict__ out, const RowAcc
 }
 
 // Warp-per-utterance variant (large N).
+// The same kernel with the ids of the NEXT chunk (same utterance, or the warp's next utterance) requested
+// before the current chunk's rows are walked.
+template <int NCH, int UNROLL, int MINB>
+__global__ void __launch_bounds__(kEmbedWarps * 32, MINB)
+    sif_embed_warp_prefetch_kernel(const float4* __restrict__ table4, int V, int d4, const float* __restrict__ wsrc,
+                                   const int64_t* __restrict__ ids, int64_t N, int64_t L,
+                                   float4* __restrict__ emb4, int* __restrict__ status) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kEmbedWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kEmbedWarps;
+  const char* lane_base = (const char*)(table4 + lane);
+  const unsigned row_bytes = (unsigned)d4 * 16u;
+  const bool tail = lane + 32 * (NCH - 1) < d4;
+  bool bad = false;
+  int64_t nid = (warp0 < N && lane < L) ? __ldcs(ids + warp0 * L + lane) : 0;
+  for (int64_t i = warp0; i < N; i += nwarps) {
+    RowAcc<NCH> acc;
+    acc.clear();
+    int cnt = 0;
+    const int64_t* row_ids = ids + i * L;
+    for (int64_t base = 0; base < L; base += 32) {
+      const int64_t id = nid;
+      // next chunk of this warp: the same utterance's next 32 tokens, else the next utterance's first
+      const bool same = base + 32 < L;
+      const int64_t ni = same ? i : i + nwarps;
+      const int64_t nb = same ? base + 32 : 0;
+      nid = (ni < N && nb + lane < L) ? __ldcs(ids + ni * L + nb + lane) : 0;
+      cnt += accumulate_chunk<NCH, false, UNROLL, false, true>(acc, lane_base, V, row_bytes, tail, wsrc, row_ids,
+                                                               nullptr, base, L, lane, bad, id);
+    }
+    store_row<NCH>(emb4 + (size_t)i * d4, acc, cnt, lane, d4);
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, MMB_STATUS_BAD_INDEX);
+}
+
 template <int NCH, bool EXPLICIT_W, int UNROLL, int MINB, bool WIDE>
 __global__ void __launch_bounds__(kEmbedWarps * 32, MINB)
     sif_embed_warp_kernel(const float4* __restrict__ table4, int V, int d4, int stride4,
@@ -320,7 +358,10 @@ static int launch_embed(const float* table, int64_t V, int d, const float* wsrc,
     int64_t blocks = ceil_div(N, kEmbedWarps);
     int64_t cap = (int64_t)sms * 8;
     int grid = (int)(blocks < cap ? blocks : cap);
-    static const int variant = getenv("MMB_EMBED_VARIANT") ? atoi(getenv("MMB_EMBED_VARIANT")) : 0;
+    // default: ids of the next chunk prefetched (variant 6) for the fused lookup; measured on B200, 4 M
+    // utterances: 11.83 ms plain (variant 0) -> 11.56 ms; also prefetching the next chunk's weight lookups
+    // (two chunks ahead) spills at the 64-register budget and takes 16.5 ms -- not kept
+    static const int variant = getenv("MMB_EMBED_VARIANT") ? atoi(getenv("MMB_EMBED_VARIANT")) : (EXPLICIT_W ? 0 : 6);
     static const int waves = getenv("MMB_EMBED_WAVES") ? atoi(getenv("MMB_EMBED_WAVES")) : 8;
     cap = (int64_t)sms * waves;
     grid = (int)(blocks < cap ? blocks : cap);
@@ -342,7 +383,15 @@ static int launch_embed(const float* table, int64_t V, int d, const float* wsrc,
         case 3: EMBED_LAUNCH(1, 6, false); break;
         case 4: EMBED_LAUNCH(4, 2, false); break;
         case 5: EMBED_LAUNCH(2, 3, false); break;
-        default: EMBED_LAUNCH(2, 4, false); break;
+        case 6:
+          if constexpr (!EXPLICIT_W) {
+            sif_embed_warp_prefetch_kernel<NCH, 2, 4><<<grid, kEmbedWarps * 32, 0, st>>>(
+                (const float4*)tbl, (int)V, d4, wsrc, ids, N, L, (float4*)emb, status);
+            break;
+          }
+          EMBED_LAUNCH(2, 4, false);
+          break;
+        default: EMBED_LAUNCH(2, 4, false); break;   // variant 0
       }
     }
 #undef EMBED_LAUNCH
