@@ -13,78 +13,75 @@ import _native as nv
 from _native import lib
 from sif_functions import Params, seq2weight, SIF_embedding, start_block, sif_embedding_device  # noqa: F401
 
-"""
-1. Initialize sentence embedding using the SIF algorithm over training data
-
-word_weights : a / (a + p(w)) - calculate unigram probabilities over training data
-"""
-
+# ---- word weights a / (a + p(w)) (host-side file handling; the arithmetic that matters runs in the kernels) ----
 
 def get_word_weights(word_freq_file, a=1e-3):
-    """reference sif.py:14-32 -- ``a / (a + count/N)`` from a "word count" text file."""
-    word_weights = {}
-    N = 0
-    with open(word_freq_file, 'r') as f:
-        for line in f:
-            line = line.strip()
-            if len(line) > 0:
-                line = line.split()
-                if len(line) == 2:
-                    word_weights[line[0]] = float(line[1])
-                    N += float(line[1])
-                else:
-                    print(line)
-    for key, value in word_weights.items():
-        word_weights[key] = a / (a + value / N)
-    return word_weights
+    """reference sif.py:14-32.  ``{word: a / (a + count / total)}`` from a text file of ``word count``
+    pairs; lines that do not have exactly two fields are echoed and skipped, blank lines ignored."""
+    counts = {}
+    with open(word_freq_file, 'r') as fh:
+        for raw in fh:
+            fields = raw.split()
+            if not fields:
+                continue
+            if len(fields) != 2:
+                print(fields)
+                continue
+            counts[fields[0]] = float(fields[1])
+    total = float(sum(counts.values()))
+    return {word: a / (a + c / total) for word, c in counts.items()}
 
 
-def load_weights(args):
-    """reference sif.py:34-42."""
-    if args['dataset'] == 'mosi':
-        return load_mosi_weights()
-    elif args['dataset'] == 'pom':
-        return load_pom_weights()
-    elif args['dataset'] == 'iemocap':
-        return load_iemocap_weights()
-    else:
-        raise NotImplementedError
+_WEIGHT_FILES = {'pom': 'pom/pom_word_weights.npy', 'iemocap': 'iemocap/iemocap_word_weights.npy'}
+
+
+def _load_weight_vector(path):
+    vec = np.load(path).squeeze()
+    print(vec.shape)
+    return vec
 
 
 def load_pom_weights():
-    """reference sif.py:44-47."""
-    weights = np.load('pom/pom_word_weights.npy').squeeze()
-    print(weights.shape)
-    return weights
+    """reference sif.py:44-47 -- the per-vocabulary weight vector shipped with the POM ids."""
+    return _load_weight_vector(_WEIGHT_FILES['pom'])
 
 
 def load_iemocap_weights():
     """reference sif.py:49-52."""
-    weights = np.load('iemocap/iemocap_word_weights.npy').squeeze()
-    print(weights.shape)
-    return weights
+    return _load_weight_vector(_WEIGHT_FILES['iemocap'])
 
 
 def load_mosi_weights(word2ix=None):
-    """reference sif.py:54-76.  The reference's regeneration branch reads an undefined
-    global ``word2ix`` (line 63, NameError); here it is an optional argument."""
-    if os.path.isfile('word_weights.npy'):
-        return np.load('word_weights.npy', allow_pickle=False).squeeze()
+    """reference sif.py:54-76 -- the cached ``word_weights.npy`` if present, else built from the enwiki
+    counts: index i gets the weight of its (lower-cased) word, 1.0 when the word has no count.  The
+    reference's rebuild branch reads a global ``word2ix`` that is never defined (line 63: NameError);
+    here the mapping is an optional argument and its absence raises the same NameError."""
+    cache = 'word_weights.npy'
+    if os.path.isfile(cache):
+        return np.load(cache, allow_pickle=False).squeeze()
     if word2ix is None:
-        raise NameError("name 'word2ix' is not defined")   # what the reference does here
-    word_weights = get_word_weights('SIF/auxiliary_data/enwiki_vocab_min200.txt')
-    weights = np.zeros((max(word2ix.values()) + 1))
-    unk = 0
+        raise NameError("name 'word2ix' is not defined")
+    by_word = get_word_weights('SIF/auxiliary_data/enwiki_vocab_min200.txt')
+    weights = np.zeros(max(word2ix.values()) + 1)
+    missing = 0
     for word, ix in word2ix.items():
-        if word.lower() not in word_weights.keys():
-            weights[ix] = 1.
-            unk += 1
-        else:
-            weights[ix] = word_weights[word.lower()]
-    print("# of words with unknown weight", unk)
+        w = by_word.get(word.lower())
+        if w is None:
+            w, missing = 1., missing + 1
+        weights[ix] = w
+    print("# of words with unknown weight", missing)
     print(weights[:5])
-    np.save('word_weights.npy', weights, allow_pickle=False)
+    np.save(cache, weights, allow_pickle=False)
     return weights
+
+
+def load_weights(args):
+    """reference sif.py:34-42 -- the weight vector of ``args['dataset']``; unknown names raise
+    NotImplementedError like the reference's final ``else``."""
+    loaders = {'mosi': load_mosi_weights, 'pom': load_pom_weights, 'iemocap': load_iemocap_weights}
+    if args['dataset'] not in loaders:
+        raise NotImplementedError
+    return loaders[args['dataset']]()
 
 
 def get_sentence_word_weights(text, weights):
