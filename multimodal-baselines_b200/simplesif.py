@@ -188,6 +188,8 @@ class GraphedStep(object):
         self.epoch_graphs = {}
         self.mmb_ops = mmb_ops
         self.moments = _dataset_moments(args, dataset)
+        self.fork = str(args.get('graph_fork', os.environ.get('MMB_GRAPH_FORK', '1'))) not in ('0', 'False', 'false', '')
+        self.side = torch.cuda.Stream(device=device) if self.fork else None
 
     def _gather(self, j):
         """``dataset[j]`` (reference utils.py:231-233 / 248-251) as one multi-tensor gather launch."""
@@ -220,8 +222,23 @@ class GraphedStep(object):
         x = self._gather(j)                       # batched gather of the device-resident tensors
         _, batch_data, batch_masks = _batch_dicts(self.args, x, getattr(self.dataset, 'table', None))
         e = _RowGather.apply(self.embeddings, j)
+        word_fn = self.word_prob_fn
+        if self.fork:
+            # The word term (vocabulary-sized products) and the heads + Gaussian terms only meet in the final
+            # sum, and each of their kernels fills a fraction of the GPU: issue the word term on a second
+            # stream, forked from and joined back into this one, so that the captured graph has two parallel
+            # branches (autograd runs each branch's backward on the stream of its forward).
+            main = torch.cuda.current_stream(self.device)
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                word_lp = self.word_prob_fn(e, batch_data['text_weights'], batch_data['text'], batch_masks['text'])
+
+            def word_fn(latents, word_weights, sent_embeddings, mask):
+                main.wait_stream(self.side)
+                word_lp.record_stream(main)
+                return word_lp
         out = self.gen_model(e)
-        log_prob = -get_log_prob_matrix(self.args, e, out, batch_data, batch_masks, self.word_prob_fn,
+        log_prob = -get_log_prob_matrix(self.args, e, out, batch_data, batch_masks, word_fn,
                                         device=self.device, verbose=False)
         if self.extra_loss is not None:
             log_prob = self.extra_loss(j, e, log_prob)
