@@ -188,8 +188,13 @@ class GraphedStep(object):
         self.epoch_graphs = {}
         self.mmb_ops = mmb_ops
         self.moments = _dataset_moments(args, dataset)
-        self.fork = str(args.get('graph_fork', os.environ.get('MMB_GRAPH_FORK', '1'))) not in ('0', 'False', 'false', '')
-        self.side = torch.cuda.Stream(device=device) if self.fork else None
+        # single-step graphs fork the word term (0.149 -> 0.124 ms per MOSI step); whole-epoch graphs do not by
+        # default: with 21 forked steps chained per graph and the graphs re-captured for every grid point, the
+        # 4-config sweep took 16.4-17.0 s forked against 12.5-14.9 s unforked on the same box
+        off = ('0', 'False', 'false', '')
+        self.fork = str(args.get('graph_fork', os.environ.get('MMB_GRAPH_FORK', '1'))) not in off
+        self.fork_epoch = str(args.get('graph_fork_epoch', os.environ.get('MMB_GRAPH_FORK_EPOCH', '0'))) not in off
+        self.side = torch.cuda.Stream(device=device) if (self.fork or self.fork_epoch) else None
 
     def _gather(self, j):
         """``dataset[j]`` (reference utils.py:231-233 / 248-251) as one multi-tensor gather launch."""
@@ -218,25 +223,29 @@ class GraphedStep(object):
             return (j, ds.text_ids[j]) + tuple(got)
         return (j,) + tuple(self.mmb_ops.gather_multi([getattr(ds, n) for n in names], j))
 
-    def _step(self, j):
+    def _step(self, j, fork=None):
+        fork = self.fork if fork is None else fork
         x = self._gather(j)                       # batched gather of the device-resident tensors
         _, batch_data, batch_masks = _batch_dicts(self.args, x, getattr(self.dataset, 'table', None))
         e = _RowGather.apply(self.embeddings, j)
-        word_fn = self.word_prob_fn
-        if self.fork:
-            # The word term (vocabulary-sized products) and the heads + Gaussian terms only meet in the final
-            # sum, and each of their kernels fills a fraction of the GPU: issue the word term on a second
-            # stream, forked from and joined back into this one, so that the captured graph has two parallel
-            # branches (autograd runs each branch's backward on the stream of its forward).
-            main = torch.cuda.current_stream(self.device)
+        # The word term (vocabulary-sized products) and the heads + Gaussian terms only meet in the final sum,
+        # and each of their kernels fills a fraction of the GPU.  The word term is issued first -- with `fork`
+        # on a second stream, forked from and joined back into this one, so that the captured graph has two
+        # parallel branches (autograd runs each branch's backward on the stream of its forward).  The order
+        # of the autograd nodes, hence every rounding, is the same with and without the fork.
+        main = torch.cuda.current_stream(self.device)
+        if fork:
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side):
                 word_lp = self.word_prob_fn(e, batch_data['text_weights'], batch_data['text'], batch_masks['text'])
+        else:
+            word_lp = self.word_prob_fn(e, batch_data['text_weights'], batch_data['text'], batch_masks['text'])
 
-            def word_fn(latents, word_weights, sent_embeddings, mask):
+        def word_fn(latents, word_weights, sent_embeddings, mask):
+            if fork:
                 main.wait_stream(self.side)
                 word_lp.record_stream(main)
-                return word_lp
+            return word_lp
         out = self.gen_model(e)
         log_prob = -get_log_prob_matrix(self.args, e, out, batch_data, batch_masks, word_fn,
                                         device=self.device, verbose=False)
@@ -331,7 +340,7 @@ class GraphedStep(object):
         with torch.cuda.stream(side):
             for n in sorted(set(sizes)) * 2:          # warm every batch size (allocator, lazy inits)
                 self.optimizer.zero_grad(set_to_none=True)
-                self._step(static_flat[:n])
+                self._step(static_flat[:n], self.fork_epoch)
         torch.cuda.current_stream(self.device).wait_stream(side)
         self._restore(params, saved, bufs)
         self.status.zero_()
@@ -348,7 +357,7 @@ class GraphedStep(object):
             off = 0
             for n in sizes:
                 self.optimizer.zero_grad(set_to_none=True)
-                total = total + self._step(static_flat[off:off + n])
+                total = total + self._step(static_flat[off:off + n], self.fork_epoch)
                 off += n
         return graph, static_flat, total
 
