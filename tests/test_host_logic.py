@@ -174,3 +174,82 @@ def test_bench_gpu_arm_refuses_to_run_without_cuda():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode != 0
     assert not [l for l in r.stdout.splitlines() if l.strip().startswith('{')]
+
+
+def test_epoch_index_helpers_draw_like_the_dataloader():
+    """The graph-replay loops never iterate the DataLoader; they take its index batches from the batch sampler.
+    That is only equivalent if the helpers consume torch's global generator exactly as `for x in loader` does
+    (one base-seed draw per iterator, then the RandomSampler's seed) -- batch order and the generator state
+    afterwards must match, for shuffled and unshuffled loaders, over several epochs."""
+    import torch
+    from torch.utils.data import DataLoader, TensorDataset
+    import simplesif
+    import sentiment_model
+
+    class Rows(TensorDataset):
+        def __getitem__(self, i):
+            return i, self.tensors[0][i]
+
+    ds = Rows(torch.arange(23.))
+    for shuffle in (True, False):
+        for helper in (lambda l: [b.tolist() for b in simplesif._epoch_index_batches(l, 'cpu')],
+                       lambda l: [b.tolist() for b in sentiment_model._index_batches(l, 'cpu')],
+                       lambda l: (lambda f, s: [f[sum(s[:k]):sum(s[:k + 1])].tolist() for k in range(len(s))])(
+                           *simplesif._epoch_indices(l, 'cpu')),
+                       lambda l: (lambda f, s: [f[sum(s[:k]):sum(s[:k + 1])].tolist() for k in range(len(s))])(
+                           *sentiment_model._epoch_indices(l, 'cpu'))):
+            loader = DataLoader(ds, batch_size=5, shuffle=shuffle)
+            torch.manual_seed(11)
+            want = [[j.tolist() for j, _ in loader] for _ in range(3)]
+            want_next = torch.rand(1)
+            torch.manual_seed(11)
+            got = [helper(loader) for _ in range(3)]
+            got_next = torch.rand(1)
+            assert got == want, (shuffle, got[0], want[0])
+            assert torch.equal(got_next, want_next)
+    assert sorted(sum(want[0], [])) == list(range(23)) and [len(b) for b in want[0]] == [5, 5, 5, 5, 3]
+
+
+def test_id_dataset_and_moment_batches_keep_the_reference_tuple_layout():
+    """Host wiring of the two step-side extensions: `MMDataIds` returns the
+    reference's tuple positions (utils.py:231-233) with ids in the text slot, `_batch_dicts` wraps them as
+    TokenIds and builds the six MMB2 modalities from base parts, and `_with_moments` swaps the Gaussian inputs
+    for per-utterance moments without touching the word term's inputs."""
+    import torch
+    import losses
+    import simplesif
+    import utils
+    N, L, d, A, Vd, V = 6, 4, 8, 3, 2, 10
+    g = torch.Generator().manual_seed(0)
+    table = torch.randn(V, d, generator=g)
+    ids = torch.randint(0, V, (N, L), generator=g)
+    aud, vis = torch.randn(N, L, A, generator=g), torch.randn(N, L, Vd, generator=g)
+    masks = {'covarep': torch.ones(N, L, A), 'facet': torch.ones(N, L, Vd)}
+    ds = utils.MMDataIds(ids, aud, vis, masks, torch.rand(V, generator=g), table, 'cpu')
+    assert len(ds) == N and ds.text_mask.shape == (N, L) and ds.text_weights.shape == (N, L)
+    j = torch.tensor([4, 1, 2])
+    x = ds[j]
+    assert len(x) == 8 and x[1].dtype == torch.int64 and torch.equal(x[1], ids[j])
+    args = {'dataset': 'mosi', 'unimodal': False}
+    _, data, bmasks = simplesif._batch_dicts(args, x, ds.table)
+    assert isinstance(data['text'], losses.TokenIds) and data['text'].shape == (3, L, d)
+    assert torch.equal(data['text'].materialize(), table[ids[j]])
+    assert set(data) == {'text', 'audio', 'visual', 'text_weights', 'audiovisual', 'textaudio', 'textvisual',
+                         'textaudiovisual'}
+    assert [type(p).__name__ for p in data['textaudiovisual'].parts] == ['TokenIds', 'Tensor', 'Tensor']
+    assert torch.equal(bmasks['text'], (ids[j] != 0).float())
+    # moments: the Gaussian slots become MomentStats rows, masks None, the word term's inputs stay
+    mom = {k: losses.MomentStats(torch.zeros(N, 3, F)) for k, F in (('audio', A), ('visual', Vd), ('text_gauss', d))}
+    xm = simplesif._with_moments(args, x, mom)
+    _, data, bmasks = simplesif._batch_dicts(args, xm, ds.table)
+    assert isinstance(data['audio'], losses.MomentStats) and data['audio'].stats.shape == (3, 3, A)
+    assert bmasks['audio'] is None and isinstance(data['text'], losses.TokenIds)
+    assert [type(p).__name__ for p in data['textaudiovisual'].parts] == ['MomentStats'] * 3
+    assert [s.shape[-1] for s in losses._segments(data['textaudiovisual'], bmasks['textaudiovisual'])] == [d, A, Vd]
+    # POM layout: aligned text in slots 8 / 9
+    dse = utils.MMDataExtraIds(ids, aud, vis, dict(masks, text_align=torch.ones(N, L, d)), torch.rand(V), table,
+                               torch.randn(N, L, d), 'cpu')
+    xe = simplesif._with_moments({'dataset': 'pom', 'unimodal': False}, dse[j], mom)
+    assert len(xe) == 10 and isinstance(xe[8], losses.MomentStats) and xe[9] is None
+    _, data, _ = simplesif._batch_dicts({'dataset': 'pom', 'unimodal': False}, xe, dse.table)
+    assert isinstance(data['text'], losses.TokenIds) and isinstance(data['textaudio'].parts[0], losses.MomentStats)
