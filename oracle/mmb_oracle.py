@@ -55,6 +55,30 @@ def normal_log_prob_grads(mu, log_sigma, values, mask):
     return lp, dmu, ds
 
 
+def gauss_moments(values, mask):
+    """Masked moments over time: ``S0 = sum_t m``, ``mean = sum_t m x / S0``,
+    ``M2 = sum_t m (x - mean)^2``, stacked (B, 3, D); ``S0 = 0`` gives mean = M2 = 0.  The identity the CUDA
+    path (mmb_gauss_moments / mmb_gauss_ll_stats) rests on: ``sum_t m (x - mu)^2 = M2 + S0 (mean - mu)^2``."""
+    x = np.asarray(values, dtype=np.float64)
+    m = np.asarray(mask, dtype=np.float64)
+    s0 = m.sum(1)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        mean = np.where(s0 != 0, (m * x).sum(1) / s0, 0.0)
+    m2 = (m * (x - mean[:, None, :]) ** 2).sum(1)
+    return np.stack([s0, mean, m2], axis=1)
+
+
+def normal_log_prob_from_moments(mu, log_sigma, stats):
+    """A7 and its gradients (as ``normal_log_prob_grads``) evaluated from ``gauss_moments`` alone."""
+    mu = np.asarray(mu, dtype=np.float64)
+    s = np.asarray(log_sigma, dtype=np.float64)
+    s0, mean, m2 = (np.asarray(stats, dtype=np.float64)[:, k, :] for k in range(3))
+    inv_var = np.exp(-2.0 * s)
+    q = m2 + s0 * (mean - mu) ** 2
+    lp = (-(LOG_SQRT_2PI + s) * s0 - 0.5 * q * inv_var).sum(-1)
+    return lp, s0 * (mean - mu) * inv_var, -s0 + q * inv_var
+
+
 # --------------------------------------------------------------------------- A8
 def _cos_rows(a, b, eps=1e-8):
     """torch ``nn.CosineSimilarity(dim=-1)``: each vector divided by ``max(norm, eps)``."""
