@@ -143,6 +143,44 @@ def word_log_prob_grad(latents, word_embeddings, word_weights, sent_embeddings, 
     return g
 
 
+def word_log_prob_grad_from_ids(latents, word_embeddings, word_weights, ids, mask, a, eps=1e-8):
+    """The algebra of mmb_word_ll_ids restated: when the token vectors are rows of the
+    table (``sent = W[ids]``), the token cosines are entries of the (B, V) cosine matrix ``C`` of the partition
+    term and the token part of the gradient is a scatter into the (B, V) coefficient matrix ``M`` of the one
+    product ``M @ W``:  ``M[b,v] = DZ_b h(C[b,v]) iw_v + sum_{t: id_t = v} r_t iw_v``,
+    ``grad_b = (M_b @ W - (DZ_b HC_b + RC_b) e_hat_b) / ||e_b||``.  Returns (lp (B,), grad (B,d))."""
+    e = np.asarray(latents, dtype=np.float64)
+    W = np.asarray(word_embeddings, dtype=np.float64)
+    ww = np.asarray(word_weights, dtype=np.float64)
+    ids = np.asarray(ids)
+    mask = np.asarray(mask, dtype=np.float64)
+    m = mask[:, :, 0] if mask.ndim == 3 else mask
+    ne = np.maximum(np.linalg.norm(e, axis=-1, keepdims=True), eps)
+    eh = e / ne
+    iw = 1.0 / np.maximum(np.linalg.norm(W, axis=-1), eps)
+    C = (e @ W.T) / ne * iw[None, :]
+    S = 1.0 - np.arccos(C) / np.pi
+    with np.errstate(divide='ignore', invalid='ignore'):
+        H = 1.0 / (np.pi * np.sqrt(1.0 - C * C))
+    Z = S.sum(-1, keepdims=True)
+    HC = (H * C).sum(-1)
+    alpha = 1.0 / (a * Z + 1.0)
+    rows = np.arange(e.shape[0])[:, None]
+    ct, st = C[rows, ids], S[rows, ids]
+    p = alpha * ww + (1.0 - alpha) * st / Z
+    lp = (np.log(p) * m).sum(-1)
+    dlp_dp = m / p
+    dp_dZ = (-a * alpha * alpha) * (ww - st / Z) - (1.0 - alpha) * st / (Z * Z)
+    DZ = (dlp_dp * dp_dZ).sum(-1)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        rr = dlp_dp * (1.0 - alpha) / Z / (np.pi * np.sqrt(1.0 - ct * ct))
+    RC = (rr * ct).sum(-1)
+    M = DZ[:, None] * H * iw[None, :]
+    np.add.at(M, (np.broadcast_to(rows, ids.shape), ids), rr * iw[ids])
+    grad = (M @ W - (DZ * HC + RC)[:, None] * eh) / ne
+    return lp, grad
+
+
 # --------------------------------------------------------------------------- A6
 MMB1_MODALITIES = ('audio', 'visual')
 MMB2_MODALITIES = ('audio', 'visual', 'audiovisual', 'textaudio', 'textvisual', 'textaudiovisual')
