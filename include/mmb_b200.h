@@ -64,6 +64,12 @@ MMB_API int mmb_version(void);
 MMB_API const char* mmb_last_error(void);
 /* sm_count / cc_major / cc_minor of the current device (any pointer may be NULL). */
 MMB_API int mmb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Instrumentation (no reference counterpart): number of kernels this library has launched in
+ * this process so far (every launch site counts itself), and the template-expanded name of the
+ * kernel a run-time dispatch chose last (tag 0 = the embed kernel of mmb_sif_embed /
+ * mmb_weighted_average).  bench.py derives `gpu_launches` and `roofline.kernel` from these. */
+MMB_API unsigned long long mmb_launch_count(void);
+MMB_API const char* mmb_last_kernel(int tag);
 /* Pinned host memory for the *_host entry points and for e2e benchmarks. */
 MMB_API int mmb_host_alloc(void** ptr, size_t bytes);
 MMB_API int mmb_host_free(void* ptr);
@@ -135,6 +141,10 @@ MMB_API int mmb_sif_embedding_host(const float* table_dev, int64_t V, int d, con
                            const double* Omega_host, void* emb_host, int emb_f64,
                            float* pc_host, int gram_mode, int64_t chunk_rows);
 
+/* The *_host entry points take their staging buffers from a private stream-ordered pool per device
+ * that keeps freed blocks for the next call; this returns all but `keep_bytes` of them to the driver. */
+MMB_API int mmb_host_pipeline_trim(size_t keep_bytes);
+
 /* ---------------------------------------------------------------- multi-GPU */
 /* The reference has no distributed code; utterances shard over the GPUs of one box and the only
  * exchange is the sum of the per-rank Grams (and, for N < d, of the start blocks).  These entry
@@ -153,9 +163,16 @@ MMB_API int mmb_comm_free(void* buf);
 MMB_API int mmb_comm_export(void* buf, void* handle64);
 MMB_API int mmb_comm_open(const void* handle64, void** peer_buf);
 MMB_API int mmb_comm_close(void* peer_buf);
-/* x (n elements, float32 or float64 when is_f64 != 0; n * elem size <= 512 KiB) <- sum over ranks. */
+/* x (n elements, float32 or float64 when is_f64 != 0; n * elem size <= 4 MiB) <- sum over ranks,
+ * in rank order (identical bits everywhere).  Besides the Gram this carries the flat head-parameter
+ * gradient of the data-parallel MMB step (843,400 floats, SURVEY 8e "MMB training") and the
+ * cross-rank BatchNorm statistics.  Cooperative launch, grid-stride.                          */
 MMB_API int mmb_allreduce_peer(void* x, int64_t n, int is_f64, int rank, int world, void* const* bufs,
                                uint64_t epoch, int* status, mmb_stream_t stream);
+/* A rank that cannot take part in the exchange of `epoch` (it failed before its mmb_*_peer call)
+ * tells its peers so: their wait ends at once with MMB_STATUS_COMM_TIMEOUT instead of after ~4 s.
+ * The communicator is unusable afterwards.                                                     */
+MMB_API int mmb_comm_abort(int rank, int world, void* const* bufs, uint64_t epoch, mmb_stream_t stream);
 /* mmb_gram followed by the all-reduce of G: on the tcgen05 path the cross-CTA reduction of the
  * Gram partials and the cross-rank exchange are ONE kernel.  N may be 0 on a rank.           */
 MMB_API int mmb_gram_allreduce_peer(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_bytes,

@@ -32,6 +32,8 @@ SIGNATURES = {
     'mmb_version': (_i, []),
     'mmb_last_error': (C.c_char_p, []),
     'mmb_device_info': (_i, [C.POINTER(_i)] * 3),
+    'mmb_launch_count': (C.c_ulonglong, []),
+    'mmb_last_kernel': (C.c_char_p, [_i]),
     'mmb_host_alloc': (_i, [C.POINTER(_p), _sz]),
     'mmb_host_free': (_i, [_p]),
     'mmb_seq2weight': (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p]),
@@ -48,6 +50,8 @@ SIGNATURES = {
     'mmb_sif_embedding_host': (_i, [_p, _i64, _i, _p, _p, _i64, _i64, _i, _p, _p, _i, _p, _i, _i64]),
     'mmb_sif_embedding_host_peer': (_i, [_p, _i64, _i, _p, _p, _i64, _i64, _i, _p, _p, _i, _p, _i, _i64, _i64, _i, _i,
                                          _p, C.c_uint64]),
+    'mmb_host_pipeline_trim': (_i, [_sz]),
+    'mmb_comm_abort': (_i, [_i, _i, _p, C.c_uint64, _p]),
     'mmb_comm_bytes': (_sz, []),
     'mmb_comm_alloc': (_i, [C.POINTER(_p)]),
     'mmb_comm_free': (_i, [_p]),

@@ -23,6 +23,18 @@ int cuda_fail(cudaError_t e, const char* what) {
   return MMB_E_CUDA;
 }
 
+static unsigned long long g_launches = 0;
+static char g_last_kernel[8][160];   // last kernel name recorded per stage tag (see note_kernel)
+
+void count_launch(const char*) { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+// Kernels chosen by a run-time dispatch record their (template-expanded) name here so that the
+// caller can say WHICH instantiation ran: tag 0 = embed.
+void note_kernel(int tag, const char* name) {
+  if (tag < 0 || tag >= 8) return;
+  strncpy(g_last_kernel[tag], name, sizeof(g_last_kernel[tag]) - 1);
+}
+
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 148;
   int dev = 0;
@@ -70,6 +82,10 @@ using namespace mmb;
 extern "C" int mmb_version(void) { return 100; }
 
 extern "C" const char* mmb_last_error(void) { return g_err; }
+
+extern "C" unsigned long long mmb_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+extern "C" const char* mmb_last_kernel(int tag) { return (tag >= 0 && tag < 8) ? g_last_kernel[tag] : ""; }
 
 extern "C" int mmb_device_info(int* sm, int* cc_major, int* cc_minor) {
   int dev = 0;
@@ -178,12 +194,41 @@ extern "C" int mmb_sif_embedding(const float* table, int64_t V, int d, const flo
 
 // ---- the same call with host buffers --------------------------------------------------------
 namespace {
+// Staging memory of the *_host entry points comes from a PRIVATE stream-ordered pool per device whose
+// release threshold keeps freed blocks for the next call (repeated calls do not pay cudaMalloc again).
+// The device's default pool -- and with it every other user of cudaMallocAsync in the process -- is left
+// alone; mmb_host_pipeline_trim() hands the cached blocks back to the driver.
+cudaMemPool_t g_host_pool[64] = {};
+
+int host_pool(cudaMemPool_t* out) {
+  int dev = 0;
+  MMB_CUDA(cudaGetDevice(&dev));
+  MMB_REQUIRE(dev >= 0 && dev < 64, "device ordinal out of range");
+  if (!g_host_pool[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool;
+    MMB_CUDA(cudaMemPoolCreate(&pool, &props));
+    uint64_t keep = UINT64_MAX;
+    MMB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    g_host_pool[dev] = pool;
+  }
+  *out = g_host_pool[dev];
+  return MMB_OK;
+}
+
 struct DevBuf {
   void* p = nullptr;
   cudaStream_t st = nullptr;
   int alloc(size_t bytes, cudaStream_t s) {
     st = s;
-    MMB_CUDA(cudaMallocAsync(&p, bytes ? bytes : 16, s));
+    cudaMemPool_t pool;
+    int rc = host_pool(&pool);
+    if (rc) return rc;
+    MMB_CUDA(cudaMallocFromPoolAsync(&p, bytes ? bytes : 16, pool, s));
     return MMB_OK;
   }
   ~DevBuf() {
@@ -204,6 +249,11 @@ struct Streams {
     ev.push_back(*e);
     return MMB_OK;
   }
+  void sync_all() {
+    if (in) cudaStreamSynchronize(in);
+    if (out) cudaStreamSynchronize(out);
+    if (comp) cudaStreamSynchronize(comp);
+  }
   ~Streams() {
     for (auto e : ev) cudaEventDestroy(e);
     if (in) cudaStreamDestroy(in);
@@ -220,6 +270,26 @@ struct HostComm {
   uint64_t epoch = 0;
   int64_t n_global = 0;
 };
+
+namespace {
+// Declared AFTER the device buffers, hence destroyed BEFORE them: on every return path -- the early
+// error returns included -- copies still in flight on the H2D / D2H streams finish before the buffers
+// they use go back to the pool.
+struct SyncGuard {
+  Streams& S;
+  ~SyncGuard() { S.sync_all(); }
+};
+// Multi-GPU: a rank that fails before it has enqueued the exchange tells its peers (abort flag) instead
+// of letting them spin until the 4 s timeout.  Destroyed before SyncGuard, so the abort is synchronised too.
+struct AbortGuard {
+  const HostComm& hc;
+  cudaStream_t st;
+  bool armed;
+  ~AbortGuard() {
+    if (armed) mmb_comm_abort(hc.rank, hc.world, hc.bufs, hc.epoch, (mmb_stream_t)st);
+  }
+};
+}  // namespace
 
 static int sif_embedding_host_impl(const float* table_dev, int64_t V, int d, const float* vocab_w_dev,
                                    const int64_t* x_host, int64_t N, int64_t L, int npc,
@@ -238,18 +308,12 @@ static int sif_embedding_host_impl(const float* table_dev, int64_t V, int d, con
   const int64_t nchunks = ceil_div(N, chunk_rows);
   const int k = npc + 10;
 
-  {  // keep freed blocks in the pool so repeated calls do not pay cudaMalloc again
-    int dev = 0;
-    MMB_CUDA(cudaGetDevice(&dev));
-    cudaMemPool_t pool;
-    MMB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-    uint64_t keep = UINT64_MAX;
-    MMB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  }
   Streams S;
   int rc = S.init();
   if (rc) return rc;
   DevBuf ids[2], emb, ws, omega, status, pcv, f64[2], gchunk;
+  SyncGuard sync_guard{S};
+  AbortGuard abort_guard{hc, S.comp, dist && npc > 0};
   const bool chunked_gram = npc > 0 && nchunks > 1;
   const size_t ids_chunk = (size_t)chunk_rows * L * sizeof(int64_t);
   if ((rc = ids[0].alloc(ids_chunk, S.comp))) return rc;
@@ -329,6 +393,7 @@ static int sif_embedding_host_impl(const float* table_dev, int64_t V, int d, con
       rc = mmb_allreduce_peer(G, (int64_t)d * d, 0, hc.rank, hc.world, hc.bufs, hc.epoch, (int*)status.p,
                               (mmb_stream_t)S.comp);
       if (rc) return rc;
+      abort_guard.armed = false;   // this rank has taken part in the exchange
     }
     const double* S0 = (const double*)omega.p;
     const int transposed = n_global < d;
@@ -389,6 +454,13 @@ static int sif_embedding_host_impl(const float* table_dev, int64_t V, int d, con
     set_error("index out of bounds: a token id is outside [-%lld, %lld)", (long long)V, (long long)V);
     return MMB_E_INDEX;
   }
+  return MMB_OK;
+}
+
+extern "C" int mmb_host_pipeline_trim(size_t keep_bytes) {
+  int dev = 0;
+  MMB_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && g_host_pool[dev]) MMB_CUDA(cudaMemPoolTrimTo(g_host_pool[dev], keep_bytes));
   return MMB_OK;
 }
 

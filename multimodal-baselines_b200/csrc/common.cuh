@@ -21,10 +21,17 @@ int sm_count();
     if (e__ != cudaSuccess) return ::mmb::cuda_fail(e__, #call); \
   } while (0)
 
+// Every kernel launch of the library passes through MMB_LAUNCH_CHECK (or calls count_launch()
+// itself): the launch counter behind mmb_launch_count() is how bench.py COUNTS `gpu_launches`
+// instead of asserting a constant.
+void count_launch(const char* name);
+void note_kernel(int tag, const char* name);
+
 #define MMB_LAUNCH_CHECK(name)                                    \
   do {                                                            \
     cudaError_t e__ = cudaGetLastError();                         \
     if (e__ != cudaSuccess) return ::mmb::cuda_fail(e__, name);   \
+    ::mmb::count_launch(name);                                    \
   } while (0)
 
 #define MMB_REQUIRE(cond, msg)             \

@@ -367,9 +367,10 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     gram_tc_reduce_allreduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ G,
                                     const PeerComm comm, int* __restrict__ status) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthreads = gridDim.x * blockDim.x;      // cooperative launch: the whole grid is co-resident
   float* mine = (float*)comm_slot(comm, comm.rank);
-  if (idx < kD * kD) {
+  for (int idx = tid; idx < kD * kD; idx += nthreads) {
     const int j = idx / kD, i = idx % kD;
     if (j >= i) {
       const float* p;
@@ -388,9 +389,15 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0) atomicOr(status, MMB_STATUS_COMM_TIMEOUT);
     return;
   }
-  if (idx < kD * kD) {
-    float s = 0.f;
-    for (int r = 0; r < comm.world; ++r) s += *((const volatile float*)comm_slot(comm, r) + idx);
+  for (int idx = tid; idx < kD * kD; idx += nthreads) {
+    float v[kCommMaxRanks];
+#pragma unroll
+    for (int r = 0; r < kCommMaxRanks; ++r)
+      if (r < comm.world) v[r] = *((const volatile float*)comm_slot(comm, r) + idx);
+    float s = v[0];
+#pragma unroll
+    for (int r = 1; r < kCommMaxRanks; ++r)
+      if (r < comm.world) s += v[r];
     G[idx] = s;
   }
 }
@@ -500,8 +507,13 @@ int gram_tc_allreduce(const float* X, int64_t N, int d, float* G, void* ws, size
   int n_cta = 0;
   const int rc = gram_tc_main(X, N, d, ws, ws_bytes, st, &n_cta);
   if (rc) return rc;
-  gram_tc_reduce_allreduce_kernel<<<(kD * kD + 255) / 256, 256, 0, st>>>((const float*)ws, n_cta, G, comm, status);
-  MMB_LAUNCH_CHECK("gram_tc_reduce_allreduce");
+  // cooperative launch on an occupancy-bounded grid: the flag wait needs every CTA resident (peer_comm.cuh)
+  const int grid = coop_grid((const void*)gram_tc_reduce_allreduce_kernel, 256, 0, (kD * kD + 255) / 256);
+  const float* part = (const float*)ws;
+  PeerComm c = comm;
+  void* args[] = {(void*)&part, (void*)&n_cta, (void*)&G, (void*)&c, (void*)&status};
+  MMB_CUDA(cudaLaunchCooperativeKernel((const void*)gram_tc_reduce_allreduce_kernel, dim3(grid), dim3(256), args, 0, st));
+  count_launch("gram_tc_reduce_allreduce");
   return MMB_OK;
 }
 

@@ -908,6 +908,7 @@ static int pcm_run(const float* G, int d, const double* S0, int k, int npc, int 
     MMB_CUDA(cudaLaunchKernelEx(&cfg, pcm_iter_kernel<KMAX>, G, d, k, P.KP, P.DP, P.nb, (const double*)Yb[cur],
                                 Yb[cur ^ 1], Qg, (const double*)Sp[cur], Sp[cur ^ 1], it == n_iter ? 2 : 1,
                                 it == n_iter ? 1 : 0, tlog ? tlog + 16 * (it < 8 ? it : 8) : (long long*)nullptr));
+    count_launch("pcm_iter");
   }
   const int fin = (n_iter + 1) & 1;
   cfg.gridDim = dim3(1);
@@ -916,6 +917,7 @@ static int pcm_run(const float* G, int d, const double* S0, int k, int npc, int 
   MMB_CUDA(cudaLaunchKernelEx(&cfg, pcm_final_kernel<KMAX>, d, k, P.KP, P.DP, P.nb, npc, transposed,
                               (const double*)Yb[fin], (const double*)Qg, (const double*)Sp[fin], pc,
                               tlog ? tlog + 16 * 10 : (long long*)nullptr));
+  count_launch("pcm_final");
   return MMB_OK;
 }
 

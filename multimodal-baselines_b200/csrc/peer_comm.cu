@@ -6,24 +6,74 @@ namespace mmb {
 int gram_tc_allreduce(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_bytes, const PeerComm& comm,
                       int* status, cudaStream_t st);
 bool gram_tc_supported(int64_t N, int d);
+int coop_grid(const void* kernel, int threads, size_t smem, int64_t want);
+
+// Grid-stride, cooperative (see comm_wait): copy x into this rank's slot, publish, wait, then
+// x[i] = sum over ranks (rank order) of slot_r[i].  V = T or a 16-byte vector of T.
+template <typename T>
+struct Vec16;
+template <> struct Vec16<float> { typedef float4 type; static constexpr int n = 4; };
+template <> struct Vec16<double> { typedef double2 type; static constexpr int n = 2; };
+__device__ __forceinline__ float4 vadd(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ double2 vadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-    peer_allreduce_kernel(T* __restrict__ x, int n, const PeerComm comm, int* __restrict__ status) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    peer_allreduce_kernel(T* __restrict__ x, int64_t n, const PeerComm comm, int* __restrict__ status) {
+  typedef typename Vec16<T>::type V;
+  constexpr int VN = Vec16<T>::n;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const bool vec = ((uintptr_t)x % 16) == 0;
+  const int64_t nv = vec ? n / VN : 0;
   T* mine = (T*)comm_slot(comm, comm.rank);
-  if (idx < n) mine[idx] = x[idx];
+  for (int64_t i = tid; i < nv; i += nthreads) ((V*)mine)[i] = ((const V*)x)[i];
+  for (int64_t i = nv * VN + tid; i < n; i += nthreads) mine[i] = x[i];
   __syncthreads();
   comm_publish(comm);
   if (!comm_wait(comm)) {
     if (threadIdx.x == 0) atomicOr(status, MMB_STATUS_COMM_TIMEOUT);
     return;
   }
-  if (idx < n) {
-    T s = (T)0;
-    for (int r = 0; r < comm.world; ++r) s += *((const volatile T*)comm_slot(comm, r) + idx);
-    x[idx] = s;
+  for (int64_t i = tid; i < nv; i += nthreads) {
+    V v[kCommMaxRanks];
+#pragma unroll
+    for (int r = 0; r < kCommMaxRanks; ++r)
+      if (r < comm.world) v[r] = __ldcv((const V*)comm_slot(comm, r) + i);   // all peers' loads in flight (ld.cv: never a stale cached line)
+    V s = v[0];
+#pragma unroll
+    for (int r = 1; r < kCommMaxRanks; ++r)
+      if (r < comm.world) s = vadd(s, v[r]);                                      // rank order
+    ((V*)x)[i] = s;
   }
+  for (int64_t i = nv * VN + tid; i < n; i += nthreads) {
+    T s = (T)0;
+    for (int r = 0; r < comm.world; ++r) s += *((const volatile T*)comm_slot(comm, r) + i);
+    x[i] = s;
+  }
+}
+
+__global__ void peer_abort_kernel(const PeerComm comm) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    __threadfence_system();
+    for (int p = 0; p < comm.world; ++p) {
+      volatile unsigned long long* flag = (volatile unsigned long long*)((char*)comm.buf[p] + kCommFlagsOffset) +
+                                          (comm.epoch & 1ull) * kCommMaxRanks + comm.rank;
+      *flag = comm.epoch | kCommAbortBit;
+    }
+    __threadfence_system();
+  }
+}
+
+// Largest co-resident grid of `kernel` at `threads` per CTA, capped at `want` CTAs.
+int coop_grid(const void* kernel, int threads, size_t smem, int64_t want) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  if (per_sm > 4) per_sm = 4;     // the exchange is latency-bound: a few CTAs per SM are plenty
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  const int64_t g = want < cap ? want : cap;
+  return (int)(g > 0 ? g : 1);
 }
 
 static int make_comm(PeerComm* c, int rank, int world, void* const* bufs, uint64_t epoch) {
@@ -81,16 +131,24 @@ extern "C" int mmb_comm_close(void* peer_buf) {
 extern "C" int mmb_allreduce_peer(void* x, int64_t n, int is_f64, int rank, int world, void* const* bufs,
                                   uint64_t epoch, int* status, mmb_stream_t stream) {
   MMB_REQUIRE(x && status && n > 0, "null pointer / empty vector");
-  MMB_REQUIRE((size_t)n * (is_f64 ? 8 : 4) <= kCommSlotBytes, "vector larger than the exchange slot (512 KiB)");
+  MMB_REQUIRE((size_t)n * (is_f64 ? 8 : 4) <= kCommSlotBytes, "vector larger than the exchange slot (4 MiB)");
   PeerComm c;
   int rc = make_comm(&c, rank, world, bufs, epoch);
   if (rc) return rc;
-  const int grid = (int)ceil_div(n, 256);
-  if (is_f64)
-    peer_allreduce_kernel<double><<<grid, 256, 0, as_stream(stream)>>>((double*)x, (int)n, c, status);
-  else
-    peer_allreduce_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((float*)x, (int)n, c, status);
-  MMB_LAUNCH_CHECK("peer_allreduce");
+  const void* fn = is_f64 ? (const void*)peer_allreduce_kernel<double> : (const void*)peer_allreduce_kernel<float>;
+  const int grid = coop_grid(fn, 256, 0, ceil_div(n, 256 * (is_f64 ? 2 : 4)));
+  void* args[] = {(void*)&x, (void*)&n, (void*)&c, (void*)&status};
+  MMB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, 0, as_stream(stream)));
+  count_launch("peer_allreduce");
+  return MMB_OK;
+}
+
+extern "C" int mmb_comm_abort(int rank, int world, void* const* bufs, uint64_t epoch, mmb_stream_t stream) {
+  PeerComm c;
+  int rc = make_comm(&c, rank, world, bufs, epoch);
+  if (rc) return rc;
+  peer_abort_kernel<<<1, 32, 0, as_stream(stream)>>>(c);
+  MMB_LAUNCH_CHECK("peer_abort");
   return MMB_OK;
 }
 

@@ -24,10 +24,17 @@
 namespace mmb {
 
 constexpr int kCommMaxRanks = 8;
-constexpr size_t kCommSlotBytes = 512 * 1024;   // >= d * d * 4 for d <= 360, and d * 32 * 8
+// One slot holds the largest vector exchanged in one call: the d x d Gram (360 KB at d = 300), the
+// N < d start block, and the flat head-parameter gradient of the data-parallel MMB step (843,400
+// floats = 3.4 MB for MMB2).
+constexpr size_t kCommSlotBytes = 4 * 1024 * 1024;
+constexpr unsigned long long kCommAbortBit = 1ull << 63;   // flag value = epoch | abort: the rank gave up
 constexpr size_t kCommFlagsOffset = 2 * kCommSlotBytes;
 constexpr size_t kCommCounterOffset = kCommFlagsOffset + 2 * kCommMaxRanks * sizeof(unsigned long long);
 constexpr size_t kCommBytes = kCommCounterOffset + 256;
+
+// Largest co-resident grid of `kernel` (threads per CTA, dynamic smem), capped at `want` CTAs.
+int coop_grid(const void* kernel, int threads, size_t smem, int64_t want);
 
 struct PeerComm {
   void* buf[kCommMaxRanks];   // buf[rank] is this rank's own buffer
@@ -61,7 +68,13 @@ __device__ __forceinline__ void comm_publish(const PeerComm& c) {
 }
 
 // Every CTA: wait until all ranks' data of this epoch is complete.  Returns false after
-// ~4 s without progress (a peer died): the caller sets MMB_STATUS_COMM_TIMEOUT and returns.
+// ~4 s without progress (a peer died) or as soon as a peer signals an abort (mmb_comm_abort): the
+// caller sets MMB_STATUS_COMM_TIMEOUT and returns.
+//
+// The waiting CTAs depend on the LAST-arriving local CTA raising the flags, so the whole grid must be
+// co-resident: every kernel that calls comm_wait is launched with cudaLaunchCooperativeKernel on a
+// grid no larger than the occupancy API allows (coop_grid() in peer_comm.cu) and strides over its
+// elements -- a concurrent kernel on another stream can delay the launch, never deadlock it.
 __device__ __forceinline__ bool comm_wait(const PeerComm& c) {
   __shared__ int ok_s;
   if (threadIdx.x == 0) ok_s = 1;
@@ -70,7 +83,10 @@ __device__ __forceinline__ bool comm_wait(const PeerComm& c) {
     volatile unsigned long long* flag =
         (volatile unsigned long long*)((char*)c.buf[c.rank] + kCommFlagsOffset) + (c.epoch & 1ull) * kCommMaxRanks + threadIdx.x;
     const long long t0 = clock64();
-    while (*flag != c.epoch) {
+    for (;;) {
+      const unsigned long long f = *flag;
+      if (f == c.epoch) break;
+      if (f == (c.epoch | kCommAbortBit)) { ok_s = 0; break; }     // the peer failed before the exchange
       if (clock64() - t0 > 8000000000ll) { ok_s = 0; break; }
       __nanosleep(64);
     }

@@ -70,29 +70,50 @@ struct RowAcc {
   }
 };
 
-// One gathered row: v[c] = row[lane + 32 c] (coalesced 16-byte loads through the read-only path).
-// `tail` = this lane takes part in the last, partial chunk (d4 not a multiple of 32); the other
-// lanes neither load nor accumulate that chunk.
+// Which of a lane's NCH row chunks (float4 index lane + 32 c) exist, i.e. lie below d4.
+//   NCH <= 4 (exact instantiations: d4 in (32 (NCH-1), 32 NCH]): chunks 0..NCH-2 are always whole, only
+//     the last one is partial -> one predicate `tail`;
+//   NCH == 8 (serves every d4 in 129..256): any chunk may be absent -> a bit per chunk.
+// Absent chunks are neither loaded (they would lie beyond the row, for the last rows beyond the table)
+// nor accumulated nor stored.
+template <int NCH> struct Live { typedef bool type; };
+template <> struct Live<8> { typedef unsigned type; };
 template <int NCH>
-__device__ __forceinline__ void load_row(float4 (&v)[NCH], const char* __restrict__ lane_base, size_t off,
-                                         bool tail) {
-  const float4* p = (const float4*)(lane_base + off);
+__device__ __forceinline__ typename Live<NCH>::type make_live(int lane, int d4) {
+  if constexpr (NCH <= 4) {
+    return lane + 32 * (NCH - 1) < d4;
+  } else {
+    unsigned m = 0;
 #pragma unroll
-  for (int c = 0; c + 1 < NCH; ++c) v[c] = __ldg(p + 32 * c);
-  if (tail) v[NCH - 1] = __ldg(p + 32 * (NCH - 1));
+    for (int c = 0; c < NCH; ++c) m |= (lane + 32 * c < d4 ? 1u : 0u) << c;
+    return m;
+  }
 }
 template <int NCH>
-__device__ __forceinline__ void fma_row(RowAcc<NCH>& acc, const float4 (&v)[NCH], float w, bool tail) {
+__device__ __forceinline__ bool chunk_on(typename Live<NCH>::type live, int c) {
+  if constexpr (NCH <= 4) return c + 1 < NCH ? true : live;
+  else return (live >> c) & 1u;
+}
+
+// One gathered row: v[c] = row[lane + 32 c] (coalesced 16-byte loads through the read-only path).
+template <int NCH>
+__device__ __forceinline__ void load_row(float4 (&v)[NCH], const char* __restrict__ lane_base, size_t off,
+                                         typename Live<NCH>::type live) {
+  const float4* p = (const float4*)(lane_base + off);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+    if (chunk_on<NCH>(live, c)) v[c] = __ldg(p + 32 * c);
+}
+template <int NCH>
+__device__ __forceinline__ void fma_row(RowAcc<NCH>& acc, const float4 (&v)[NCH], float w,
+                                        typename Live<NCH>::type live) {
   const f32x2 ww = pack2(w, w);
 #pragma unroll
-  for (int c = 0; c + 1 < NCH; ++c) {
-    ffma2(acc.a[c][0], ww, pack2(v[c].x, v[c].y));
-    ffma2(acc.a[c][1], ww, pack2(v[c].z, v[c].w));
-  }
-  if (tail) {
-    ffma2(acc.a[NCH - 1][0], ww, pack2(v[NCH - 1].x, v[NCH - 1].y));
-    ffma2(acc.a[NCH - 1][1], ww, pack2(v[NCH - 1].z, v[NCH - 1].w));
-  }
+  for (int c = 0; c < NCH; ++c)
+    if (chunk_on<NCH>(live, c)) {
+      ffma2(acc.a[c][0], ww, pack2(v[c].x, v[c].y));
+      ffma2(acc.a[c][1], ww, pack2(v[c].z, v[c].w));
+    }
 }
 
 // Byte offset of a table row: 32-bit when the whole table is < 4 GiB (one IMAD per token-lane,
@@ -116,7 +137,7 @@ template <> struct RowOff<true> { typedef unsigned long long type; };
 // depend on them.
 template <int NCH, bool EXPLICIT_W, int UNROLL, bool WIDE, bool PRE = false>
 __device__ __forceinline__ int accumulate_chunk(RowAcc<NCH>& acc, const char* __restrict__ lane_base,
-                                                int V, unsigned row_bytes, bool tail,
+                                                int V, unsigned row_bytes, typename Live<NCH>::type tail,
                                                 const float* __restrict__ wsrc,
                                                 const int64_t* __restrict__ row_ids,
                                                 const float* __restrict__ row_w, int64_t base,
@@ -237,7 +258,7 @@ __global__ void __launch_bounds__(kEmbedWarps * 32, MINB)
   const int64_t nwarps = (int64_t)gridDim.x * kEmbedWarps;
   const char* lane_base = (const char*)(table4 + lane);
   const unsigned row_bytes = (unsigned)d4 * 16u;
-  const bool tail = lane + 32 * (NCH - 1) < d4;
+  const typename Live<NCH>::type tail = make_live<NCH>(lane, d4);
   bool bad = false;
   int64_t nid = (warp0 < N && lane < L) ? __ldcs(ids + warp0 * L + lane) : 0;
   for (int64_t i = warp0; i < N; i += nwarps) {
@@ -271,7 +292,7 @@ __global__ void __launch_bounds__(kEmbedWarps * 32, MINB)
   const int64_t nwarps = (int64_t)gridDim.x * kEmbedWarps;
   const char* lane_base = (const char*)(table4 + lane);
   const unsigned row_bytes = (unsigned)stride4 * 16u;   // table row pitch (>= d4 float4)
-  const bool tail = lane + 32 * (NCH - 1) < d4;
+  const typename Live<NCH>::type tail = make_live<NCH>(lane, d4);
   bool bad = false;
   for (int64_t i = warp0; i < N; i += nwarps) {
     RowAcc<NCH> acc;
@@ -301,7 +322,7 @@ __global__ void __launch_bounds__(kEmbedWarps * 32)
   const int warp = threadIdx.x >> 5;
   const char* lane_base = (const char*)(table4 + lane);
   const unsigned row_bytes = (unsigned)d4 * 16u;
-  const bool tail = lane + 32 * (NCH - 1) < d4;
+  const typename Live<NCH>::type tail = make_live<NCH>(lane, d4);
   bool bad = false;
   for (int64_t i = blockIdx.x; i < N; i += gridDim.x) {
     RowAcc<NCH> acc;
@@ -315,7 +336,7 @@ __global__ void __launch_bounds__(kEmbedWarps * 32)
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-      if ((NCH <= 4 && c + 1 < NCH) || tail) {
+      if (chunk_on<NCH>(tail, c)) {
         unpack2(acc.a[c][0], r.x, r.y);
         unpack2(acc.a[c][1], r.z, r.w);
       }
@@ -349,7 +370,9 @@ static int launch_embed(const float* table, int64_t V, int d, const float* wsrc,
   const int sms = sm_count();
   const int d4 = d / 4;
   const bool few_long = (L >= 256) && (N < (int64_t)sms * 16);
+  char kname[96] = "";
   if (few_long) {
+    snprintf(kname, sizeof(kname), "sif_embed_cta_kernel<%d,%s>", NCH, EXPLICIT_W ? "true" : "false");
     int grid = (int)(N < (int64_t)sms * 8 ? N : (int64_t)sms * 8);
     sif_embed_cta_kernel<NCH, EXPLICIT_W><<<grid, kEmbedWarps * 32, 0, st>>>(
         (const float4*)table, (int)V, d4, wsrc, ids, N, L, (float4*)emb, status);
@@ -372,9 +395,18 @@ static int launch_embed(const float* table, int64_t V, int d, const float* wsrc,
     const int stride4 = d4;
     const bool wide = (uint64_t)V * (uint64_t)stride4 * 16u >= ((uint64_t)1 << 32);
 #define EMBED_LAUNCH(U, B, W)                                                                \
-  sif_embed_warp_kernel<NCH, EXPLICIT_W, U, B, W><<<grid, kEmbedWarps * 32, 0, st>>>(        \
-      (const float4*)tbl, (int)V, d4, stride4, wsrc, ids, N, L, (float4*)emb, status)
-    if (wide) {
+  do {                                                                                       \
+    sif_embed_warp_kernel<NCH, EXPLICIT_W, U, B, W><<<grid, kEmbedWarps * 32, 0, st>>>(      \
+        (const float4*)tbl, (int)V, d4, stride4, wsrc, ids, N, L, (float4*)emb, status);     \
+    snprintf(kname, sizeof(kname), "sif_embed_warp_kernel<%d,%s,%d,%d,%s>", NCH,             \
+             EXPLICIT_W ? "true" : "false", U, B, W ? "true" : "false");                     \
+  } while (0)
+    if constexpr (NCH > 4) {
+      // d in 516..1024: 16 accumulator + 32 row registers per row in flight -- one row in flight at
+      // 2 CTAs per SM (128 registers) instead of spilling at the d = 300 configuration
+      if (wide) EMBED_LAUNCH(1, 2, true);
+      else EMBED_LAUNCH(1, 2, false);
+    } else if (wide) {
       EMBED_LAUNCH(2, 4, true);
     } else {
       switch (variant) {
@@ -384,9 +416,10 @@ static int launch_embed(const float* table, int64_t V, int d, const float* wsrc,
         case 4: EMBED_LAUNCH(4, 2, false); break;
         case 5: EMBED_LAUNCH(2, 3, false); break;
         case 6:
-          if constexpr (!EXPLICIT_W) {
+          if constexpr (!EXPLICIT_W && NCH <= 4) {
             sif_embed_warp_prefetch_kernel<NCH, 2, 4><<<grid, kEmbedWarps * 32, 0, st>>>(
                 (const float4*)tbl, (int)V, d4, wsrc, ids, N, L, (float4*)emb, status);
+            snprintf(kname, sizeof(kname), "sif_embed_warp_prefetch_kernel<%d,2,4>", NCH);
             break;
           }
           EMBED_LAUNCH(2, 4, false);
@@ -397,6 +430,7 @@ static int launch_embed(const float* table, int64_t V, int d, const float* wsrc,
 #undef EMBED_LAUNCH
   }
   MMB_LAUNCH_CHECK("sif_embed");
+  note_kernel(0, kname);
   return MMB_OK;
 }
 

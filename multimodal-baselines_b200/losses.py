@@ -111,7 +111,11 @@ def _segments(values, mask):
 def _exit_if_nonfinite(status, names):
     """reference losses.py:258-264: a non-finite log-probability prints and exits.  With a status
     sink installed (mmb_ops.set_status_sink, the graph-captured loop) the check is deferred to the
-    caller's next synchronisation point (check_status_sink)."""
+    caller's next synchronisation point (check_status_sink).
+
+    Deliberately stricter than the reference: its test ``lp.min().abs() == np.inf`` fires only when the
+    batch minimum is -inf (or everything is +inf) and never on NaN (``NaN == inf`` is False), so the
+    reference keeps training on NaN latents; the kernels flag ANY non-finite value (inf or NaN)."""
     if mmb_ops.status_deferred():
         return
     if int(status.item()) & 2:
@@ -162,13 +166,17 @@ def get_word_log_prob_angular(latents, weights, word_embeddings, data, mask, a):
     return get_word_log_prob_angular2(latents, word_embeddings, weights[data], word_embeddings[data], mask, a)
 
 
-def get_word_log_prob_angular2(latents, word_embeddings, word_weights, sent_embeddings, mask, a):
+def get_word_log_prob_angular2(latents, word_embeddings, word_weights, sent_embeddings, mask, a, status=None):
     """reference losses.py:68-95 -- Ethayarajh-style angular word log-probability.
 
     latents (B, d); word_embeddings (V, d); word_weights (B, L); sent_embeddings (B, L, d);
     mask (B, L, d) (only ``mask[:, :, 0]`` is used, line 90) or (B, L).  Returns (B,).
+    ``status`` (extra, optional): the int32 device word that receives MMB_STATUS_NONFINITE when a
+    log-probability is not finite; the caller that passes it checks it (simplesif's closure does, like
+    reference simplesif.py:529-535).
     """
-    status = mmb_ops.new_status(latents.device)
+    if status is None:
+        status = mmb_ops.new_status(latents.device)
     if isinstance(sent_embeddings, TokenIds):
         same_table = (sent_embeddings.table.data_ptr() == word_embeddings.data_ptr()
                       and sent_embeddings.table.shape == word_embeddings.shape)

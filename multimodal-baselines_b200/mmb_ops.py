@@ -6,6 +6,7 @@ word term) or one more library call (heads).  Inputs are made float32 / contiguo
 tensors; anything else is an error -- there is no CPU fallback.
 """
 import ctypes as C
+import weakref
 
 import torch
 
@@ -314,15 +315,26 @@ def new_status(device):
 
 
 def table_inv_norm(table):
-    """1 / max(||row||, 1e-8) of the word table (torch CosineSimilarity's clamp), cached while the
-    same tensor version is passed again -- the table is a constant of the optimisation loop."""
-    key = (table.data_ptr(), tuple(table.shape), table._version, str(table.device))
-    hit = _INV_NORM_CACHE.get('k')
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    """1 / max(||row||, 1e-8) of the word table (torch CosineSimilarity's clamp), cached per table
+    TENSOR OBJECT (weak reference + ``_version``) -- the table is a constant of the optimisation loop.
+    The key is the object, not its address: a new table of the same shape that the caching allocator
+    places at a freed table's address must not inherit the old norms.  Several tables can be cached
+    at once; an entry dies with its table.  Callers that bake the returned buffer into a CUDA graph
+    must keep their own reference to it (``GraphedStep`` does)."""
+    key = id(table)
+    hit = _INV_NORM_CACHE.get(key)
+    if hit is not None and hit[0]() is table and hit[1] == table._version:
+        return hit[2]
     V, d = table.shape
     inv_norm = torch.empty(V, dtype=torch.float32, device=table.device)
     nv.check(lib.mmb_row_inv_norm(nv.ptr(table), V, d, nv.ptr(inv_norm), nv.stream_ptr()))
     if not torch.cuda.is_current_stream_capturing():
-        _INV_NORM_CACHE['k'] = (key, inv_norm)
+        ref = weakref.ref(table, lambda _r, k=key: _INV_NORM_CACHE.pop(k, None))
+        _INV_NORM_CACHE[key] = (ref, table._version, inv_norm)
     return inv_norm
+
+
+def cached_inv_norms():
+    """The inverse-norm buffers currently cached (GraphedStep keeps them alive for as long as its graphs,
+    which have their addresses baked in, can be replayed)."""
+    return [hit[2] for hit in _INV_NORM_CACHE.values()]

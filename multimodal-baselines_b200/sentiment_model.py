@@ -90,8 +90,12 @@ def _epoch_indices(loader, device):
 
 
 def _l1(model, latents, labels, j):
+    # nn.L1Loss(reduce=False) of the reference (sentiment_model.py:90, 103): plain broadcasting of the
+    # squeezed prediction against the label batch.  For (B,) or (B, n_out) labels that is element-wise;
+    # for (B, 1) labels the reference's (B,) prediction broadcasts to (B, B) -- reproduced, not "fixed",
+    # because the downstream MAE / correlation of such a run depend on it.
     senti = labels[j]
-    return (model(latents[j]).reshape(senti.shape) - senti).abs(), senti
+    return (model(latents[j]) - senti).abs(), senti
 
 
 def predict_sentiment(data, model, latents):
@@ -103,10 +107,10 @@ def predict_sentiment(data, model, latents):
     with torch.no_grad():
         for j in _index_batches(data, labels.device):
             senti = labels[j]
-            p = model(latents[j]).reshape(senti.shape)
-            total += (p - senti).abs().sum()
+            p = model(latents[j])                    # squeezed, as the reference feeds it to L1Loss and cat
+            total += (p - senti).abs().sum()         # broadcasts like nn.L1Loss(reduce=False)
             ys.append(senti)
-            ps.append(p)
+            ps.append(p.reshape(1) if p.dim() == 0 else p)   # (a batch of one: the reference's cat would raise)
     print("MAE: {}".format(float(total) / len(data.dataset)))
     return torch.cat(ps).cpu().numpy(), torch.cat(ys).cpu().numpy()
 

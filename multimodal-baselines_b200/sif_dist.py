@@ -42,6 +42,72 @@ def allreduce_sum_(t, group=None):
     return t
 
 
+_NUMA_NOTE = 'not bound (single process)'
+
+
+def _gpu_numa_node(local_rank):
+    """NUMA node of GPU `local_rank` from sysfs (None when the guest hides it: numa_node = -1)."""
+    try:
+        prop = torch.cuda.get_device_properties(local_rank)
+        bdf = '%04x:%02x:%02x.0' % (getattr(prop, 'pci_domain_id', 0), prop.pci_bus_id, prop.pci_device_id)
+        with open('/sys/bus/pci/devices/%s/numa_node' % bdf) as fh:
+            node = int(fh.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def _node_cpus(node):
+    with open('/sys/devices/system/node/node%d/cpulist' % node) as fh:
+        cpus = set()
+        for part in fh.read().strip().split(','):
+            if '-' in part:
+                a, b = part.split('-')
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: pin this process's threads (and, by first touch, the pinned host buffers it
+    allocates afterwards) to the NUMA node its GPU hangs off, so that eight ranks' H2D/D2H streams do not
+    all cross one socket's memory controller.  A no-op, recorded in ``numa_note()``, when the box shows a
+    single node or hides the GPU's node (virtualised guests report numa_node = -1)."""
+    global _NUMA_NOTE
+    try:
+        n_nodes = len([d for d in os.listdir('/sys/devices/system/node') if d.startswith('node') and d[4:].isdigit()])
+    except Exception:
+        n_nodes = 0
+    node = _gpu_numa_node(local_rank)
+    if n_nodes <= 1 or node is None:
+        _NUMA_NOTE = 'no placement possible: %d NUMA node(s) visible, GPU %d reports node %s' % (n_nodes, local_rank, node)
+        return None
+    try:
+        allowed = os.sched_getaffinity(0)
+        cpus = _node_cpus(node) & allowed
+        if not cpus:
+            _NUMA_NOTE = 'GPU %d is on node %d but none of its CPUs are in this cpuset' % (local_rank, node)
+            return None
+        os.sched_setaffinity(0, cpus)
+        # MPOL_PREFERRED on the GPU's node for every later allocation of this process (set_mempolicy, x86-64 238)
+        try:
+            libc = C.CDLL(None, use_errno=True)
+            mask = C.c_ulong(1 << node)
+            libc.syscall(C.c_long(238), C.c_int(1), C.byref(mask), C.c_ulong(64))
+        except Exception:
+            pass
+        _NUMA_NOTE = 'rank bound to NUMA node %d of GPU %d (%d CPUs, MPOL_PREFERRED)' % (node, local_rank, len(cpus))
+        return node
+    except Exception as e:
+        _NUMA_NOTE = 'binding failed: %s' % e
+        return None
+
+
+def numa_note():
+    return _NUMA_NOTE
+
+
 class PeerComm(object):
     """NVLink exchange buffers of the ranks of one box (one process per GPU).
 
@@ -87,7 +153,7 @@ class PeerComm(object):
         return C.c_uint64(self.epoch)
 
     def allreduce_(self, t):
-        """In-place sum over ranks of a small float32 / float64 CUDA tensor (<= 512 KiB)."""
+        """In-place sum over ranks of a float32 / float64 CUDA tensor (<= 4 MiB), rank order, identical bits."""
         nv = self.nv
         assert t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.float64)
         nv.check(self.lib.mmb_allreduce_peer(nv.ptr(t), t.numel(), int(t.dtype == torch.float64), self.rank,
@@ -172,11 +238,23 @@ def close_default_comms():
     _DEFAULT_COMM.clear()
 
 
+def local_omega_rows(n_global, lo, n_local, npc, start_block_fn):
+    """Rows [lo, lo + n_local) of the global seeded Omega (N_global x (npc+10), float64): the host-side
+    partition rule of the N < d case (each rank multiplies ITS rows of X^T with ITS rows of Omega)."""
+    return np.ascontiguousarray(start_block_fn(n_global, npc)[lo:lo + n_local])
+
+
 def local_start_block(emb_local, n_global, lo, npc, start_block_fn):
     """N_global < d: this rank's share of S0 = X^T Omega, using rows [lo, hi) of the global
     seeded Omega (float64, d x (npc+10)); the caller all-reduces it."""
-    omega = torch.as_tensor(start_block_fn(n_global, npc)[lo:lo + emb_local.shape[0]]).to(emb_local.device)
-    return emb_local.double().T @ omega
+    import _native as nv
+    n_local, d = emb_local.shape
+    k = npc + 10
+    S0 = torch.zeros((d, k), dtype=torch.float64, device=emb_local.device)
+    if n_local > 0:
+        omega = torch.as_tensor(local_omega_rows(n_global, lo, n_local, npc, start_block_fn)).to(emb_local.device)
+        nv.check(nv.lib.mmb_start_block_xt(nv.ptr(emb_local), n_local, d, nv.ptr(omega), k, nv.ptr(S0), nv.stream_ptr()))
+    return S0
 
 
 def sharded_sif_embedding(table_t, vocab_w_t, ids_local_t, n_global, lo, npc=1, group=None, gram_mode=0,

@@ -165,7 +165,13 @@ def _compute_pc_device(X_t, npc, mode=nv.GRAM_AUTO):
 def compute_pc(X, npc=1):
     """reference sif_functions.py:58-67 -- the ``components_`` of scikit-learn's
     ``TruncatedSVD(n_components=npc, n_iter=7, random_state=0).fit(X)`` (no centring),
-    computed from the d x d Gram on the device; float64 (npc, d)."""
+    computed from the d x d Gram on the device; float64 (npc, d).
+
+    Precision note: the reference keeps X in float64 end to end (sif_functions.py:58-81 receive the
+    float64 array of line 37); here X is rounded to float32 on upload, the Gram is accumulated in
+    FP32 / 3xTF32 and only the d x (npc+10) solve runs in FP64.  The result is returned as float64 for
+    type parity, but carries float32 input rounding (cos > 0.9999 against sklearn's float64 output is
+    what the parity tests assert, north_star's tolerance)."""
     dev = nv.require_cuda()
     as_np = _is_np(X)
     X_t = nv.to_device(X, torch.float32, dev)
@@ -183,7 +189,8 @@ def project_out(X_t, pc_t, out=None):
 
 
 def remove_pc(X, npc=1):
-    """reference sif_functions.py:69-81."""
+    """reference sif_functions.py:69-81.  Like compute_pc, X is rounded to float32 on upload and the
+    projection is evaluated in FP32 (the reference works in float64); returned as float64."""
     dev = nv.require_cuda()
     as_np = _is_np(X)
     X_t = nv.to_device(X, torch.float32, dev)

@@ -186,6 +186,7 @@ class GraphedStep(object):
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.graphs = {}
         self.epoch_graphs = {}
+        self._keepalive = []
         self.mmb_ops = mmb_ops
         self.moments = _dataset_moments(args, dataset)
         # single-step graphs fork the word term (0.149 -> 0.124 ms per MOSI step); whole-epoch graphs do not by
@@ -308,6 +309,7 @@ class GraphedStep(object):
         with torch.cuda.graph(graph):
             static_loss = self._step(static_j)
         # the capture itself does not execute; state is untouched
+        self._keepalive.extend(self.mmb_ops.cached_inv_norms())   # buffers whose addresses the graph holds
         return graph, static_j, static_loss
 
     def __call__(self, j):
@@ -359,6 +361,7 @@ class GraphedStep(object):
                 self.optimizer.zero_grad(set_to_none=True)
                 total = total + self._step(static_flat[off:off + n], self.fork_epoch)
                 off += n
+        self._keepalive.extend(self.mmb_ops.cached_inv_norms())
         return graph, static_flat, total
 
     def run_epoch(self, flat, sizes):
@@ -511,8 +514,18 @@ def make_word_log_prob_fn(args, weights, word_embeddings, a=1e-3):
         raise NotImplementedError
 
     def get_word_log_prob2(latents, word_weights, sent_embeddings, mask):
-        # the inf check of reference 529-535 is the kernel's status word (losses.py)
-        return word_log_prob_fn(latents, word_embeddings, word_weights, sent_embeddings, mask, a)
+        if word_log_prob_fn is not get_word_log_prob_angular2:
+            return word_log_prob_fn(latents, word_embeddings, word_weights, sent_embeddings, mask, a)
+        # the inf check of reference 529-535: the kernel raises a bit in `status`; read here (one sync,
+        # as in the reference) unless a status sink defers it to the epoch's end (graph-captured loop)
+        status = mmb_ops.new_status(latents.device)
+        word_log_prob = word_log_prob_fn(latents, word_embeddings, word_weights, sent_embeddings, mask, a,
+                                         status=status)
+        if not mmb_ops.status_deferred() and int(status.item()) & 2:
+            print('word inf')
+            print(latents.size())
+            sys.exit()
+        return word_log_prob
     return get_word_log_prob2
 
 

@@ -277,15 +277,18 @@ SENTIMENT_CASES = {
     'mosi': dict(dataset='mosi', n_out=1, early_stopping=False, seed=81),
     'pom': dict(dataset='pom', n_out=3, early_stopping=False, seed=82),
     'mosi_early_stopping': dict(dataset='mosi', n_out=1, early_stopping=True, seed=83),
+    # (N, 1) label layout: the reference's squeezed (B,) prediction broadcasts against (B, 1) labels
+    # to a (B, B) L1 matrix (sentiment_model.py:90-103) -- reproduced, see sentiment_model._l1
+    'mosi_column_labels': dict(dataset='mosi', n_out=1, early_stopping=False, seed=84, column_labels=True),
 }
 
 
-def sentiment_inputs(dataset, n_out, early_stopping, seed, d=30, sizes=(150, 45, 70)):
+def sentiment_inputs(dataset, n_out, early_stopping, seed, d=30, sizes=(150, 45, 70), column_labels=False):
     rng = np.random.default_rng(seed)
     lat = [rng.standard_normal((n, d)).astype(np.float32) for n in sizes]
     U = rng.standard_normal((d, n_out))
     labs = [(np.tanh(x @ U) * 3 + 0.3 * rng.standard_normal((len(x), n_out))).astype(np.float32) for x in lat]
-    if n_out == 1:
+    if n_out == 1 and not column_labels:
         labs = [y[:, 0] for y in labs]
     args = {'dataset': dataset, 'sentiment_hidden_size': 20, 'n_sentiment_epochs': 95, 'sentiment_lr': 0.1,
             'early_stopping': early_stopping, 'lr_decay': 0.5}

@@ -37,7 +37,9 @@ def _worker(rank, world, port, n_global, d, q):
     Xl = torch.as_tensor(X[lo:hi])
     G = (Xl.T @ Xl).float()
     sif_dist.allreduce_sum_(G)
-    S0 = sif_dist.local_start_block(Xl, n_global, lo, 1, so.start_block)
+    # the rank's share of S0 = X^T Omega: its rows of X against ITS rows of the global seeded Omega (the product
+    # itself is mmb_start_block_xt on the GPU; here the partition rule is what is under test)
+    S0 = Xl.double().T @ torch.as_tensor(sif_dist.local_omega_rows(n_global, lo, hi - lo, 1, so.start_block))
     sif_dist.allreduce_sum_(S0)
     q.put((rank, lo, hi, G.numpy(), S0.numpy()))
     dist.barrier()

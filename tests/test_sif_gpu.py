@@ -51,11 +51,11 @@ def test_golden_pipeline(mods, golden_dir, name):
     assert float(np.dot(pc[0], g['pc'][0])) > PC_COS                 # sign convention too
     emb = sif.get_sentence_embeddings(We, weights, ids)
     assert emb.dtype == np.float64
-    assert rel_err(emb[:64], g['emb']) < 5 * EMB_RTOL
+    assert rel_err(emb[:64], g['emb']) < EMB_RTOL
     p = sf.Params()
     p.rmpc = 1
     emb2 = sf.SIF_embedding(We, ids, w, p)
-    assert rel_err(emb2[:64], g['emb']) < 5 * EMB_RTOL
+    assert rel_err(emb2[:64], g['emb']) < EMB_RTOL
     p.rmpc = 0
     assert rel_err(sf.SIF_embedding(We, ids, w, p)[:64], g['avg']) < EMB_RTOL
 
@@ -73,7 +73,7 @@ def test_golden_pom_real_ids(mods, golden_dir):
     avg = sf.get_weighted_average(We, ids, w)                        # CTA-per-utterance kernel
     assert rel_err(avg, g['avg']) < EMB_RTOL
     emb = sif.get_sentence_embeddings(We, g['weights'], ids)
-    assert rel_err(emb, g['emb']) < 5 * EMB_RTOL
+    assert rel_err(emb, g['emb']) < EMB_RTOL
 
 
 @pytest.mark.parametrize('tag', list(cases.PC_CASES))
@@ -97,7 +97,8 @@ def test_compute_pc_matches_sklearn(mods, golden_dir, tag, npc):
 
 @pytest.mark.parametrize('n,L,V,d', [(1, 1, 5, 300), (7, 33, 50, 300), (300, 64, 1000, 300),
                                      (513, 20, 3016, 300), (40, 700, 400, 300), (65, 5, 30, 64),
-                                     (33, 9, 30, 512), (3, 300, 20, 128)])
+                                     (33, 9, 30, 512), (3, 300, 20, 128),
+                                     (33, 9, 30, 640), (5, 300, 20, 768), (200, 64, 500, 1024), (9, 260, 12, 516)])
 def test_embed_shapes_vs_oracle(mods, n, L, V, d):
     """Ragged/edge shapes, both kernel variants (warp- and CTA-per-utterance), d != 300."""
     nv, sf, sif = mods
@@ -108,7 +109,16 @@ def test_embed_shapes_vs_oracle(mods, n, L, V, d):
     w = sf.seq2weight(ids, np.ones(ids.shape), weights)
     np.testing.assert_array_equal(w, so.seq2weight(ids, np.ones(ids.shape), weights))
     avg = sf.get_weighted_average(We, ids, w)
-    assert rel_err(avg, so.get_weighted_average(We, ids, w)) < EMB_RTOL
+    want = so.get_weighted_average(We, ids, w)
+    assert rel_err(avg, want) < EMB_RTOL
+    # the fused lookup + gather (mmb_sif_embed: the prefetching warp kernel for d <= 512, the one-row-in-flight
+    # configuration above) on the same ids, including the table's last rows
+    import torch
+    dev = torch.device('cuda')
+    fused = sf.sif_embedding_device(torch.as_tensor(We, dtype=torch.float32, device=dev),
+                                    torch.as_tensor(weights.astype(np.float32), device=dev),
+                                    torch.as_tensor(ids, device=dev), npc=0)
+    assert rel_err(fused.double().cpu().numpy(), want) < EMB_RTOL
 
 
 def test_quirks(mods):
@@ -206,7 +216,7 @@ def test_large_properties_full_size_slice(mods):
     w_rows = vw[ids[rows]].cpu().numpy()
     avg = so.get_weighted_average(table.cpu().numpy(), ids[rows].cpu().numpy(), w_rows)
     want = so.remove_pc_with(avg, pc.double().cpu().numpy())
-    assert rel_err(emb[rows].double().cpu().numpy(), want) < 5 * EMB_RTOL
+    assert rel_err(emb[rows].double().cpu().numpy(), want) < EMB_RTOL
 
 
 def test_gram_tcgen05_matches_float64(mods):
@@ -314,7 +324,7 @@ def test_golden_pom_full_splits(mods, golden_dir, split):
     pc = sf.compute_pc(avg, 1)
     assert float(np.dot(pc[0], g[split + '_pc'][0])) > PC_COS
     emb = sif.get_sentence_embeddings(We, g['weights'], ids)
-    assert rel_err(emb, g[split + '_emb'].astype(np.float64)) < 5 * EMB_RTOL
+    assert rel_err(emb, g[split + '_emb'].astype(np.float64)) < EMB_RTOL
 
 
 def test_mosi_shape_three_splits(mods):
@@ -332,7 +342,7 @@ def test_mosi_shape_three_splits(mods):
         got = sif.get_sentence_embeddings(We, weights, ids)
         want = so.get_sentence_embeddings(We, weights, ids)
         assert got.shape == (n, 300) and got.dtype == np.float64
-        assert rel_err(got, want) < 5 * EMB_RTOL, n
+        assert rel_err(got, want) < EMB_RTOL, n
 
 
 def test_embed_property_random_shapes(mods):

@@ -49,6 +49,17 @@ def main():
         got = comm.allreduce_(x.clone())
         comm.check()
         exact = torch.equal(got, want)
+        # the vector of the data-parallel MMB step: 843,400 head-parameter gradients (3.4 MB, vector path + tail)
+        for n_big, dt in ((843_401, torch.float32), (3_300, torch.float64)):
+            xb = torch.randn(n_big, device=dev, dtype=dt, generator=torch.Generator(device=dev).manual_seed(7 + rank))
+            xs = [torch.empty_like(xb) for _ in range(world)]
+            dist.all_gather(xs, xb)
+            want = xs[0].clone()
+            for r in range(1, world):
+                want += xs[r]
+            got = comm.allreduce_(xb.clone())
+            comm.check()
+            exact = exact and torch.equal(got, want)
         if n_global >= 300:
             h_ids = ids[lo:hi].cpu().numpy()
             h_out = np.empty((hi - lo, 300), dtype=np.float32)
