@@ -93,8 +93,20 @@ class HeadsFunction(torch.autograd.Function):
         need_z = ctx.needs_input_grad[0]
         need_w = any(ctx.needs_input_grad[2:])
         dz = torch.empty_like(z) if need_z else None
-        dWs = [torch.empty_like(w) for w in Ws] if need_w else None
-        dbs = [torch.empty(D, dtype=torch.float32, device=z.device) for D in ctx.Ds] if need_w else None
+        dWs = dbs = flat = None
+        if need_w:
+            # every head's dW and db are views of ONE flat buffer, in parameter order (W0, b0, W1, b1, ...): the
+            # data-parallel step sums it over the ranks with one exchange right behind the kernel that fills it
+            sizes = []
+            for w, D in zip(Ws, ctx.Ds):
+                sizes.extend([w.numel(), D])
+            flat = torch.empty(sum(sizes), dtype=torch.float32, device=z.device)
+            views, off = [], 0
+            for n_el in sizes:
+                views.append(flat[off:off + n_el])
+                off += n_el
+            dWs = [v.view_as(w) for v, w in zip(views[0::2], Ws)]
+            dbs = views[1::2]
         Ds_c = _int_array(ctx.Ds)
         nbytes = lib.mmb_heads_backward_workspace_bytes(B, d, n, Ds_c) if need_z else 0
         ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=z.device)
@@ -102,6 +114,11 @@ class HeadsFunction(torch.autograd.Function):
                                         nv.ptr(dz), _ptr_array(dWs) if need_w else None,
                                         _ptr_array(dbs) if need_w else None, nv.ptr(ws), nbytes,
                                         nv.stream_ptr()))
+        if need_w:
+            import mmb_dp
+            dp = mmb_dp.active()
+            if dp is not None and getattr(dp, 'reduce_head_grads', False):
+                dp.allreduce_(flat)          # sum over ranks of the local-batch sums (already scaled by 1 / B_global)
         grads = [dz, None]
         for h in range(n):
             grads.append(dWs[h] if need_w and ctx.needs_input_grad[2 + 2 * h] else None)

@@ -75,7 +75,16 @@ class AudioVisualGeneratorMultimodal(nn.Module):
         self.embedding_dim = self.embedding.size()[-1]
 
     def forward(self, embeddings):
-        to_gen = self.norm(embeddings) if self.norm is not None else embeddings
+        if self.norm is None:
+            to_gen = embeddings
+        else:
+            import mmb_dp
+            dp = mmb_dp.active()
+            if dp is not None and isinstance(self.norm, nn.BatchNorm1d):
+                # data-parallel step: the batch statistics are those of the GLOBAL batch (mmb_dp)
+                to_gen = mmb_dp.sync_batch_norm(self.norm, embeddings, dp)
+            else:
+                to_gen = self.norm(embeddings)
         mods = list(self.embed2out.keys())
         params, is_ls = [], []
         for mod in mods:

@@ -28,6 +28,7 @@ from torch.utils.data import DataLoader
 
 from losses import CatSegments, MomentStats, TokenIds, get_log_prob_matrix, get_word_log_prob_angular, get_word_log_prob_dot_prod  # noqa: F401
 from losses import get_word_log_prob_angular2
+import mmb_ops
 from models import AudioVisualGeneratorConcat, AudioVisualGenerator, AudioVisualGeneratorMultimodal  # noqa: F401
 from sentiment_model import SentimentData, SentimentModel, train_sentiment_for_latents
 from sif import load_weights, get_sentence_embeddings
