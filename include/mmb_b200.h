@@ -94,6 +94,23 @@ MMB_API int mmb_weighted_average(const float* table, int64_t V, int d, const int
 MMB_API int mmb_sif_embed(const float* table, int64_t V, int d, const float* vocab_w, const int64_t* x,
                   int64_t N, int64_t L, float* emb, int* status, mmb_stream_t stream);
 
+/* Ragged (CSR) ids, SURVEY.md 8f N3 -- the same result as mmb_sif_embed on the right-padded (N, L_pad)
+ * matrix the reference builds (utils.py:77-80; sif_functions.py:28-56), without walking the padding:
+ * utterance i is tokens[offsets[i] .. offsets[i+1]) (int64, offsets has N + 1 entries) and is understood
+ * to be followed by L_pad - length_i copies of `pad_id`, whose contribution the kernel adds in closed form
+ * (n_pad * vocab_w[pad_id] * table[pad_id] to the sum; n_pad to the divisor when that weight is non-zero --
+ * the reference's divisor counts every token of the padded row, sif_functions.py:55).
+ * mmb_ids_lengths / mmb_ids_compact convert a padded device matrix: length_i = 1 + index of the last token
+ * that is not pad_id (interior pad ids stay tokens); offsets = exclusive prefix sums (N + 1 entries);
+ * tokens = the rows' prefixes back to back (offsets[N] entries: read it back to size the buffer).      */
+MMB_API int mmb_sif_embed_ragged(const float* table, int64_t V, int d, const float* vocab_w,
+                                 const int64_t* tokens, const int64_t* offsets, int64_t N, int64_t L_pad,
+                                 int64_t pad_id, float* emb, int* status, mmb_stream_t stream);
+MMB_API int mmb_ids_lengths(const int64_t* ids, int64_t N, int64_t L, int64_t pad_id, int64_t* lengths,
+                            int64_t* offsets, mmb_stream_t stream);
+MMB_API int mmb_ids_compact(const int64_t* ids, int64_t N, int64_t L, const int64_t* offsets, int64_t* tokens,
+                            mmb_stream_t stream);
+
 /* compute_pc part 1 -- sif_functions.py:58-67: G = X^T X (d x d, float32), no centring.
  * `ws` is scratch of at least mmb_gram_workspace_bytes(N, d, mode) bytes.             */
 MMB_API size_t mmb_gram_workspace_bytes(int64_t N, int d, int mode);
@@ -304,6 +321,11 @@ MMB_API int mmb_closed_form_finish(int N, int L, int d, const float* sent_w, con
  * tensor); out / mask are (N, T, F_out + pos_embed_dim): value (x + min) * 2 / (max - min) - 1
  * (the reference adds the minimum), exact zeros -> -10 with mask 0, then pos_embed_dim position
  * columns with the reference's first-axis quirk and mask 1.                                 */
+/* update_masks simplesif.py:36-40: mask[i] = ids[i] != 0 as float (the (N, L, d) broadcast is a stride-0
+ * view on the caller's side); update_masks_vect simplesif.py:42-47: mask[r] = all(x[r, :] != 0) for the
+ * (N*T, F) rows of an aligned text tensor.                                                         */
+MMB_API int mmb_token_mask(const int64_t* ids, int64_t n, float* mask, mmb_stream_t stream);
+MMB_API int mmb_step_mask(const float* x, int64_t rows, int F, float* mask, mmb_stream_t stream);
 MMB_API size_t mmb_feature_minmax_workspace_bytes(int64_t rows, int F);
 MMB_API int mmb_feature_minmax(const float* x, int64_t rows, int F, float* mn, float* mx, void* ws,
                        size_t ws_bytes, mmb_stream_t stream);

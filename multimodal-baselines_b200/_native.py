@@ -39,6 +39,11 @@ SIGNATURES = {
     'mmb_seq2weight': (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p]),
     'mmb_weighted_average': (_i, [_p, _i64, _i, _p, _p, _i64, _i64, _p, _p, _p]),
     'mmb_sif_embed': (_i, [_p, _i64, _i, _p, _p, _i64, _i64, _p, _p, _p]),
+    'mmb_sif_embed_ragged': (_i, [_p, _i64, _i, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p]),
+    'mmb_ids_lengths': (_i, [_p, _i64, _i64, _i64, _p, _p, _p]),
+    'mmb_ids_compact': (_i, [_p, _i64, _i64, _p, _p, _p]),
+    'mmb_token_mask': (_i, [_p, _i64, _p, _p]),
+    'mmb_step_mask': (_i, [_p, _i64, _i, _p, _p]),
     'mmb_gram_workspace_bytes': (_sz, [_i64, _i, _i]),
     'mmb_gram': (_i, [_p, _i64, _i, _p, _p, _sz, _i, _p]),
     'mmb_pc_workspace_bytes': (_sz, [_i, _i]),

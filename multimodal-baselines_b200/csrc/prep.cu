@@ -133,3 +133,49 @@ extern "C" int mmb_prep_features(const float* x, int64_t N, int T, int F_in, con
   MMB_LAUNCH_CHECK("prep_features");
   return MMB_OK;
 }
+
+// ---- masks (reference simplesif.py:36-47), SURVEY.md 8f N3 ------------------------------------------------
+namespace mmb {
+// update_masks: text mask = (ids != 0); the reference broadcasts it to (N, L, embedding_dim) ints on the host
+// (1 GB at POM) -- here it is the (N, L) float vector, expanded as a stride-0 view by the caller.
+__global__ void token_mask_kernel(const int64_t* __restrict__ ids, int64_t n, float* __restrict__ mask) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    mask[i] = __ldcs(ids + i) != 0 ? 1.f : 0.f;
+}
+// update_masks_vect: a time step is valid iff NO feature of it is exactly 0.  Warp per (n, t) row.
+__global__ void __launch_bounds__(256)
+    step_mask_kernel(const float* __restrict__ x, int64_t rows, int F, float* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    bool ok = true;
+    for (int f = lane; f < F; f += 32) ok = ok && (__ldcs(x + r * F + f) != 0.f);
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) mask[r] = ok ? 1.f : 0.f;
+  }
+}
+}  // namespace mmb
+
+extern "C" int mmb_token_mask(const int64_t* ids, int64_t n, float* mask, mmb_stream_t stream) {
+  MMB_REQUIRE(n >= 0, "negative size");
+  if (n == 0) return MMB_OK;
+  MMB_REQUIRE(ids && mask, "null pointer");
+  const int64_t blocks = mmb::ceil_div(n, 1024);
+  const int grid = (int)(blocks < (int64_t)mmb::sm_count() * 8 ? blocks : (int64_t)mmb::sm_count() * 8);
+  mmb::token_mask_kernel<<<grid, 256, 0, mmb::as_stream(stream)>>>(ids, n, mask);
+  MMB_LAUNCH_CHECK("token_mask");
+  return MMB_OK;
+}
+
+extern "C" int mmb_step_mask(const float* x, int64_t rows, int F, float* mask, mmb_stream_t stream) {
+  MMB_REQUIRE(rows >= 0 && F > 0, "bad size");
+  if (rows == 0) return MMB_OK;
+  MMB_REQUIRE(x && mask, "null pointer");
+  const int64_t blocks = mmb::ceil_div(rows, 8);
+  const int grid = (int)(blocks < (int64_t)mmb::sm_count() * 8 ? blocks : (int64_t)mmb::sm_count() * 8);
+  mmb::step_mask_kernel<<<grid, 256, 0, mmb::as_stream(stream)>>>(x, rows, F, mask);
+  MMB_LAUNCH_CHECK("step_mask");
+  return MMB_OK;
+}

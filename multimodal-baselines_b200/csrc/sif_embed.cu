@@ -308,6 +308,139 @@ __global__ void __launch_bounds__(kEmbedWarps * 32, MINB)
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, MMB_STATUS_BAD_INDEX);
 }
 
+// Ragged (CSR) variant, SURVEY.md 8f N3: utterance i is tokens[offsets[i] .. offsets[i+1]) -- what is left of a
+// right-padded row once its trailing run of the pad id is cut off (utils.py:77-80 pads POM to 1089 / 1357
+// tokens: 73 % of that fixture is padding, 37 % of the bench workload).  The reference still sums the pad
+// tokens -- the pad id is an ordinary row with an ordinary weight (1.0 in the POM weights) and its weight
+// counts in the divisor (sif_functions.py:55) -- so their contribution is added in closed form:
+// n_pad * w[pad] * table[pad] to the sum, n_pad to the divisor when w[pad] != 0, n_pad = L_pad - length.
+// Result: the padded kernel's, up to the rounding of one multiply instead of per-chunk partial sums.
+template <int NCH, int UNROLL, int MINB>
+__global__ void __launch_bounds__(kEmbedWarps * 32, MINB)
+    sif_embed_ragged_kernel(const float4* __restrict__ table4, int V, int d4, const float* __restrict__ wsrc,
+                            const int64_t* __restrict__ tokens, const int64_t* __restrict__ offsets, int64_t N,
+                            int64_t L_pad, int64_t pad_id, float4* __restrict__ emb4, int* __restrict__ status) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kEmbedWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kEmbedWarps;
+  const char* lane_base = (const char*)(table4 + lane);
+  const unsigned row_bytes = (unsigned)d4 * 16u;
+  const typename Live<NCH>::type tail = make_live<NCH>(lane, d4);
+  bool bad = false;
+  // the pad token: weight by seq2weight's rule (negative id -> 0), row by NumPy's (negative ids wrap)
+  const int64_t pad_row = pad_id < 0 ? pad_id + V : pad_id;
+  const bool pad_ok = pad_row >= 0 && pad_row < V;
+  const float pad_w = (pad_ok && pad_id >= 0) ? __ldg(wsrc + pad_id) : 0.f;
+  for (int64_t i = warp0; i < N; i += nwarps) {
+    RowAcc<NCH> acc;
+    acc.clear();
+    int cnt = 0;
+    const int64_t o0 = __ldg(offsets + i), o1 = __ldg(offsets + i + 1);
+    const int64_t len = o1 - o0;
+    for (int64_t base = 0; base < len; base += 32)
+      cnt += accumulate_chunk<NCH, false, UNROLL, true>(acc, lane_base, V, row_bytes, tail, wsrc, tokens + o0, nullptr,
+                                                        base, len, lane, bad);
+    const int64_t n_pad = L_pad - len;
+    if (n_pad > 0) {
+      if (pad_ok) {
+        float4 v[NCH];
+        load_row<NCH>(v, lane_base, (size_t)pad_row * row_bytes, tail);
+        fma_row<NCH>(acc, v, (float)n_pad * pad_w, tail);
+        if (pad_w != 0.f) cnt += (int)n_pad;
+      } else {
+        bad = true;
+      }
+    } else if (n_pad < 0) {
+      bad = true;    // an utterance longer than the padded length it claims
+    }
+    store_row<NCH>(emb4 + (size_t)i * d4, acc, cnt, lane, d4);
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, MMB_STATUS_BAD_INDEX);
+}
+
+// padded (N, L) ids -> lengths: index of the last token that is not the pad id, plus one (interior
+// occurrences of the pad id -- MOSI's shared OOV row 0 -- stay ordinary tokens).  Warp per row.
+__global__ void __launch_bounds__(256)
+    ids_lengths_kernel(const int64_t* __restrict__ ids, int64_t N, int64_t L, int64_t pad_id,
+                       int64_t* __restrict__ lengths) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = warp0; i < N; i += nwarps) {
+    int64_t last = 0;
+    for (int64_t base = 0; base < L; base += 32) {
+      const int64_t t = base + lane;
+      const bool real = t < L && __ldcs(ids + i * L + t) != pad_id;
+      const unsigned m = __ballot_sync(0xffffffffu, real);
+      if (m) last = base + (32 - __clz(m));
+    }
+    if (lane == 0) lengths[i] = last;
+  }
+}
+
+// tokens[offsets[i] + t] = ids[i, t] for t < lengths[i].  Warp per row, coalesced both ways.
+__global__ void __launch_bounds__(256)
+    ids_compact_kernel(const int64_t* __restrict__ ids, int64_t N, int64_t L, const int64_t* __restrict__ offsets,
+                       int64_t* __restrict__ tokens) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = warp0; i < N; i += nwarps) {
+    const int64_t o0 = __ldg(offsets + i), len = __ldg(offsets + i + 1) - o0;
+    for (int64_t t = lane; t < len; t += 32) tokens[o0 + t] = __ldcs(ids + i * L + t);
+  }
+}
+
+// offsets[0] = 0, offsets[i + 1] = lengths[0] + ... + lengths[i]: one CTA, chunked scan with a running carry
+// (N is at most tens of millions and the conversion runs once per split, next to kernels that take
+// milliseconds; 1024 threads x 8 items per round).
+__global__ void __launch_bounds__(1024)
+    offsets_scan_kernel(const int64_t* __restrict__ lengths, int64_t N, int64_t* __restrict__ offsets) {
+  __shared__ long long warp_tot[32];
+  __shared__ long long carry_s;
+  constexpr int ITEMS = 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { carry_s = 0; offsets[0] = 0; }
+  __syncthreads();
+  for (int64_t base = 0; base < N; base += 1024 * ITEMS) {
+    long long v[ITEMS];
+    long long sum = 0;
+    const int64_t i0 = base + (int64_t)threadIdx.x * ITEMS;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      v[k] = (i0 + k < N) ? lengths[i0 + k] : 0;
+      sum += v[k];
+    }
+    long long incl = sum;                       // inclusive scan of the per-thread sums: warp, then CTA
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      long long w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long n = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += n;
+      }
+      warp_tot[lane] = w;                       // inclusive over warps
+    }
+    __syncthreads();
+    long long run = carry_s + (warp ? warp_tot[warp - 1] : 0) + incl - sum;    // exclusive prefix of this thread
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      run += v[k];
+      if (i0 + k < N) offsets[i0 + k + 1] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = run;
+    __syncthreads();
+  }
+}
+
 // CTA-per-utterance variant (few, long utterances -- the POM shape: 203 x 1357): the 8
 // warps take 32-token chunks round-robin and are summed through shared memory in warp
 // order, so the result is still deterministic.
@@ -484,4 +617,62 @@ extern "C" int mmb_sif_embed(const float* table, int64_t V, int d, const float* 
                              const int64_t* x, int64_t N, int64_t L, float* emb, int* status,
                              mmb_stream_t stream) {
   return dispatch_embed<false>(table, V, d, vocab_w, x, N, L, emb, status, as_stream(stream));
+}
+
+// ---- ragged (CSR) ids, SURVEY.md 8f N3 -----------------------------------------------------------------
+extern "C" int mmb_sif_embed_ragged(const float* table, int64_t V, int d, const float* vocab_w,
+                                    const int64_t* tokens, const int64_t* offsets, int64_t N, int64_t L_pad,
+                                    int64_t pad_id, float* emb, int* status, mmb_stream_t stream) {
+  MMB_REQUIRE(d > 0 && d % 4 == 0 && d <= 512, "d must be a multiple of 4, <= 512");
+  MMB_REQUIRE(V > 0 && V < (int64_t)1 << 31, "V out of range");
+  MMB_REQUIRE(N >= 0 && L_pad >= 0, "negative size");
+  if (N == 0) return MMB_OK;
+  MMB_REQUIRE(table && vocab_w && offsets && emb && status, "null pointer");
+  MMB_REQUIRE(((uintptr_t)table % 16 == 0) && ((uintptr_t)emb % 16 == 0), "table/emb must be 16-byte aligned");
+  const int sms = sm_count();
+  const int64_t blocks = ceil_div(N, kEmbedWarps);
+  const int grid = (int)(blocks < (int64_t)sms * 8 ? blocks : (int64_t)sms * 8);
+  const int d4 = d / 4;
+  cudaStream_t st = as_stream(stream);
+#define RAGGED_LAUNCH(NCH)                                                                          \
+  sif_embed_ragged_kernel<NCH, 2, 4><<<grid, kEmbedWarps * 32, 0, st>>>(                            \
+      (const float4*)table, (int)V, d4, vocab_w, tokens, offsets, N, L_pad, pad_id, (float4*)emb, status)
+  switch ((d4 + 31) / 32) {
+    case 1: RAGGED_LAUNCH(1); break;
+    case 2: RAGGED_LAUNCH(2); break;
+    case 3: RAGGED_LAUNCH(3); break;
+    default: RAGGED_LAUNCH(4); break;
+  }
+#undef RAGGED_LAUNCH
+  MMB_LAUNCH_CHECK("sif_embed_ragged");
+  note_kernel(0, "sif_embed_ragged_kernel");
+  return MMB_OK;
+}
+
+extern "C" int mmb_ids_lengths(const int64_t* ids, int64_t N, int64_t L, int64_t pad_id, int64_t* lengths,
+                               int64_t* offsets, mmb_stream_t stream) {
+  MMB_REQUIRE(N >= 0 && L >= 0, "negative size");
+  MMB_REQUIRE(offsets && (N == 0 || (lengths && (ids || L == 0))), "null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (N > 0) {
+    const int64_t blocks = ceil_div(N, 8);
+    const int grid = (int)(blocks < (int64_t)sm_count() * 8 ? blocks : (int64_t)sm_count() * 8);
+    ids_lengths_kernel<<<grid, 256, 0, st>>>(ids, N, L, pad_id, lengths);
+    MMB_LAUNCH_CHECK("ids_lengths");
+  }
+  offsets_scan_kernel<<<1, 1024, 0, st>>>(lengths, N, offsets);
+  MMB_LAUNCH_CHECK("offsets_scan");
+  return MMB_OK;
+}
+
+extern "C" int mmb_ids_compact(const int64_t* ids, int64_t N, int64_t L, const int64_t* offsets, int64_t* tokens,
+                               mmb_stream_t stream) {
+  MMB_REQUIRE(N >= 0 && L >= 0, "negative size");
+  if (N == 0 || L == 0) return MMB_OK;
+  MMB_REQUIRE(ids && offsets && tokens, "null pointer");
+  const int64_t blocks = ceil_div(N, 8);
+  const int grid = (int)(blocks < (int64_t)sm_count() * 8 ? blocks : (int64_t)sm_count() * 8);
+  ids_compact_kernel<<<grid, 256, 0, as_stream(stream)>>>(ids, N, L, offsets, tokens);
+  MMB_LAUNCH_CHECK("ids_compact");
+  return MMB_OK;
 }

@@ -12,6 +12,7 @@ import torch
 import _native as nv
 from _native import lib
 from sif_functions import Params, seq2weight, SIF_embedding, start_block, sif_embedding_device  # noqa: F401
+from sif_functions import RaggedIds, sif_embedding_ragged, to_ragged  # noqa: F401
 
 # ---- word weights a / (a + p(w)) (host-side file handling; the arithmetic that matters runs in the kernels) ----
 
@@ -99,6 +100,11 @@ def get_sentence_embeddings(word_embeddings, weights, text, out=None):
     """
     RMPC = 1
     dev = nv.require_cuda()
+    if isinstance(text, RaggedIds):
+        # CSR ids on the device -- the padded matrix's result without its padding
+        table_t = nv.to_device(word_embeddings, torch.float32, dev)
+        w_t = nv.to_device(weights, torch.float32, dev).reshape(-1)
+        return sif_embedding_ragged(table_t, w_t, text, npc=RMPC)
     if isinstance(text, torch.Tensor) and text.is_cuda:
         table_t = nv.to_device(word_embeddings, torch.float32, dev)
         w_t = nv.to_device(weights, torch.float32, dev).reshape(-1)

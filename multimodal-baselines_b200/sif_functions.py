@@ -16,7 +16,7 @@ from _native import lib
 
 __all__ = ['seq2weight', 'Params', 'get_weighted_average', 'compute_pc', 'remove_pc',
            'SIF_embedding', 'start_block', 'gram', 'pc_from_gram', 'project_out',
-           'sif_embedding_device']
+           'sif_embedding_device', 'RaggedIds', 'to_ragged', 'sif_embedding_ragged']
 
 
 def _is_np(*xs):
@@ -235,4 +235,70 @@ def sif_embedding_device(table_t, vocab_w_t, ids_t, npc=1, gram_mode=nv.GRAM_AUT
                                    gram_mode, nv.ptr(st), nv.stream_ptr()))
     if check:
         nv.raise_on_status(st, V)
+    return (emb, pc) if return_pc else emb
+
+
+# --------------------------------------------------------------------------- ragged ids
+class RaggedIds(object):
+    """Token ids in CSR form on the device: utterance i is ``tokens[offsets[i]:offsets[i+1]]`` (int64 CUDA
+    tensors; ``offsets`` has N + 1 entries), standing for row i of the right-padded ``(N, L_pad)`` id matrix
+    the reference builds (utils.py:77-80), i.e. followed by ``L_pad - length_i`` copies of ``pad_id``.  The
+    pad tokens stay part of the arithmetic (they are ordinary tokens to sif_functions.py:28-56: summed with
+    their weight, counted in the divisor) but are neither stored, moved nor walked."""
+
+    def __init__(self, tokens, offsets, L_pad, pad_id=0):
+        self.tokens, self.offsets, self.L_pad, self.pad_id = tokens, offsets, int(L_pad), int(pad_id)
+
+    @property
+    def shape(self):
+        return (int(self.offsets.numel()) - 1, self.L_pad)
+
+    def lengths(self):
+        return self.offsets[1:] - self.offsets[:-1]
+
+    def to_padded(self):
+        """The (N, L_pad) matrix back (testing / interop)."""
+        n, L = self.shape
+        out = torch.full((n, L), self.pad_id, dtype=torch.int64, device=self.tokens.device)
+        lens = self.lengths()
+        pos = torch.arange(L, device=out.device)[None, :]
+        out[pos < lens[:, None]] = self.tokens
+        return out
+
+
+def to_ragged(ids, pad_id=0, device=None):
+    """Padded ``(N, L)`` ids (NumPy or tensor) -> ``RaggedIds`` on the device (``mmb_ids_lengths`` +
+    ``mmb_ids_compact``): length = 1 + index of the last token that is not ``pad_id``; interior pad ids
+    (MOSI's shared OOV row 0) stay tokens."""
+    dev = device or nv.require_cuda()
+    ids_t = nv.to_device(ids, torch.int64, dev)
+    if ids_t.dim() != 2:
+        raise ValueError('ids must be (n_samples, seq_len)')
+    n, L = ids_t.shape
+    lengths = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    nv.check(lib.mmb_ids_lengths(nv.ptr(ids_t), n, L, int(pad_id), nv.ptr(lengths), nv.ptr(offsets), nv.stream_ptr()))
+    total = int(offsets[-1].item())
+    tokens = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+    nv.check(lib.mmb_ids_compact(nv.ptr(ids_t), n, L, nv.ptr(offsets), nv.ptr(tokens), nv.stream_ptr()))
+    return RaggedIds(tokens[:total], offsets, L, pad_id)
+
+
+def sif_embedding_ragged(table_t, vocab_w_t, ragged, npc=1, gram_mode=nv.GRAM_AUTO, return_pc=False, check=True):
+    """``sif_embedding_device`` on ``RaggedIds``: ``mmb_sif_embed_ragged`` -> Gram -> components ->
+    projection, all on the device.  Equal to the padded call on ``ragged.to_padded()``."""
+    n, _ = ragged.shape
+    V, d = table_t.shape
+    dev = table_t.device
+    emb = torch.empty((n, d), dtype=torch.float32, device=dev)
+    st = _status(dev)
+    nv.check(lib.mmb_sif_embed_ragged(nv.ptr(table_t), V, d, nv.ptr(vocab_w_t), nv.ptr(ragged.tokens),
+                                      nv.ptr(ragged.offsets), n, ragged.L_pad, ragged.pad_id, nv.ptr(emb), nv.ptr(st),
+                                      nv.stream_ptr()))
+    if check:
+        nv.raise_on_status(st, V)
+    pc = None
+    if npc > 0 and n > 0:
+        pc = _compute_pc_device(emb, npc, gram_mode)
+        project_out(emb, pc, out=emb)
     return (emb, pc) if return_pc else emb

@@ -54,6 +54,33 @@ def update_masks_vect(mask_dict, data, key='text'):
     mask_dict[key] = np.broadcast_to(np.expand_dims(tmp2, -1), data.shape)
 
 
+def update_masks_device(mask_dict, ids, embedding_dim, device=None):
+    """``update_masks`` (reference simplesif.py:36-40) on the device, SURVEY.md 8f N3: ``mask_dict['text']``
+    becomes the (N, L, embedding_dim) float32 CUDA mask as a stride-0 VIEW of the (N, L) vector ``ids != 0``
+    (``mmb_token_mask``) -- the reference materialises N * L * embedding_dim ints on the host (1 GB at POM).
+    ``MMData`` and the kernels take the view as is (only ``mask[:, :, 0]`` is ever read for the text)."""
+    import _native as nv
+    dev = device or nv.require_cuda()
+    ids_t = nv.to_device(ids, torch.int64, dev)
+    m = torch.empty(ids_t.shape, dtype=torch.float32, device=dev)
+    nv.check(nv.lib.mmb_token_mask(nv.ptr(ids_t), ids_t.numel(), nv.ptr(m), nv.stream_ptr()))
+    mask_dict['text'] = m.unsqueeze(-1).expand(*ids_t.shape, embedding_dim)
+    return mask_dict['text']
+
+
+def update_masks_vect_device(mask_dict, data, key='text', device=None):
+    """``update_masks_vect`` (reference simplesif.py:42-47) on the device: a time step is valid iff no
+    feature of it is exactly 0 (``mmb_step_mask``); the (N, T, F) mask is a stride-0 view of the (N, T) one."""
+    import _native as nv
+    dev = device or nv.require_cuda()
+    x = nv.to_device(data, torch.float32, dev)
+    N, T, F = x.shape
+    m = torch.empty((N, T), dtype=torch.float32, device=dev)
+    nv.check(nv.lib.mmb_step_mask(nv.ptr(x), N * T, F, nv.ptr(m), nv.stream_ptr()))
+    mask_dict[key] = m.unsqueeze(-1).expand(N, T, F)
+    return mask_dict[key]
+
+
 def _batch_dicts(args, x, table=None):
     """The per-step ``batch_data`` / ``batch_masks`` of reference simplesif.py:72-124, with the
     concatenated modalities expressed as CatSegments instead of materialised torch.cat.  A batch of an
@@ -163,6 +190,9 @@ class _RowGather(torch.autograd.Function):
         grad = torch.zeros((ctx.n,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
         grad.index_add_(0, j, g)
         return grad, None
+
+
+CAPTURE_SECONDS = [0.0]      # wall time spent warming up + capturing graphs (sweep.py reports it per config)
 
 
 class GraphedStep(object):
@@ -283,6 +313,13 @@ class GraphedStep(object):
 
     def _capture(self, n):
         """Warm up on a side stream (state restored afterwards), then capture a step for n rows."""
+        t0 = time.perf_counter()
+        try:
+            return self._capture_impl(n)
+        finally:
+            CAPTURE_SECONDS[0] += time.perf_counter() - t0
+
+    def _capture_impl(self, n):
         static_j = torch.zeros(n, dtype=torch.int64, device=self.device)
         params, saved, bufs = self._snapshot()
         had_state = len(self.optimizer.state) > 0
@@ -330,6 +367,13 @@ class GraphedStep(object):
     def _capture_epoch(self, sizes):
         """Capture a WHOLE epoch -- one step per batch, the batches being static slices of one index buffer
         -- as a single graph: one replay (and one small index upload) per epoch instead of one per step."""
+        t0 = time.perf_counter()
+        try:
+            return self._capture_epoch_impl(sizes)
+        finally:
+            CAPTURE_SECONDS[0] += time.perf_counter() - t0
+
+    def _capture_epoch_impl(self, sizes):
         n_total = int(sum(sizes))
         static_flat = torch.zeros(n_total, dtype=torch.int64, device=self.device)
         params, saved, bufs = self._snapshot()

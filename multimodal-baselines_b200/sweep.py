@@ -156,17 +156,29 @@ def run_config(cfg, prep, epochs_scale=1.0, cuda_graph=True, verbose=False):
     old_stdout = sys.stdout
     if not verbose:
         sys.stdout = buf
+    phase, t_last = {}, [time.perf_counter()]
+    cap0 = simplesif.CAPTURE_SECONDS[0]
+
+    def lap(name):
+        torch.cuda.synchronize(device)
+        now = time.perf_counter()
+        phase[name] = now - t_last[0]
+        t_last[0] = now
     try:
         train_embed, (train_losses, _) = simplesif.train_end_to_end(
             args, gen_model, senti_model, prep.embeddings[0], loaders[0], SentimentData(prep.labels[0], device),
             senti_mask, word_fn, device, verbose=False, validation_data=(prep.embeddings[1], loaders[1]))
+        lap('train_e2e_incl_nested_validation')
         valid_embed, _ = simplesif.optimize_latents(args, False, gen_model, prep.embeddings[1], loaders[1],
                                                     args['n_epochs'], args['lr'], word_fn, device, verbose=False)
         test_embed, (test_losses, _) = simplesif.optimize_latents(args, False, gen_model, prep.embeddings[2],
                                                                   loaders[2], args['n_epochs'], args['lr'], word_fn,
                                                                   device, verbose=False)
+        lap('valid_test_latents')
         results, _ = train_sentiment_for_latents(args, (train_embed, valid_embed, test_embed), tuple(prep.labels),
                                                  device)
+        lap('sentiment_regressor')
+        phase['graph_capture_latent_loops'] = simplesif.CAPTURE_SECONDS[0] - cap0
     except SystemExit:
         sys.stdout = old_stdout
         tail = ' | '.join(buf.getvalue().strip().splitlines()[-7:])
@@ -175,7 +187,7 @@ def run_config(cfg, prep, epochs_scale=1.0, cuda_graph=True, verbose=False):
         sys.stdout = old_stdout
     results = {k: v for k, v in results.items() if k in ('mae', 'accuracy', 'corr', 'mult_acc', 'f_score')}
     return {'config_num': cfg['config_num'], 'results': results, 'train_loss': train_losses[-1],
-            'test_loss': test_losses[-1]}
+            'test_loss': test_losses[-1], 'phase_s': {k: round(v, 3) for k, v in phase.items()}}
 
 
 def main(argv=None):

@@ -4,26 +4,117 @@
 utils.py:193-251) and are kept as in the reference: device-resident tensors, ``__getitem__``
 returns ``(idx, text, aud, vis, text_m, aud_m, vis_m, text_w[, text_a, text_a_m])``.
 ``normalize_data`` and ``add_positional_embeddings`` reproduce the reference's preprocessing
-including its quirks (see the docstrings).  The ``.h5`` loaders need ``h5py`` and the external
-datasets, neither of which ships with the reference; they raise a clear error when missing.
+including its quirks (see the docstrings).  ``load_data`` and its parts read the reference's file layout
+(``.npy`` ids / tables, ``word2ix`` pickle / JSON, ``.h5`` features -- the last needs ``h5py``); the datasets
+themselves are external downloads of the reference.
 """
 import numpy as np
 import torch
 from torch.utils.data import Dataset
 
 
-def load_data(args):
-    """reference utils.py:10-128 -- reads data/{mosi,pom,iemocap}_data.h5 (external downloads,
-    reference README.md:9) and the GloVe / id files (reference .MISSING_LARGE_BLOBS)."""
+def _h5py():
     try:
-        import h5py  # noqa: F401
+        import h5py
+        return h5py
     except ImportError as e:
-        raise ImportError("load_data needs h5py and the reference's external data files "
-                          "(data/%s_data.h5); neither is part of this repository" % args.get('dataset')) from e
-    if args['dataset'] not in ('mosi', 'pom', 'iemocap'):
-        raise ValueError('unknown dataset %r' % (args['dataset'],))
-    raise FileNotFoundError("data/%s_data.h5 is an external download of the reference and is not available here"
-                            % args['dataset'])
+        raise ImportError("the reference's feature files (data/*_data.h5, README.md:9) are HDF5: install h5py to "
+                          "read them; the id / vocabulary loaders (load_word2ix, load_text_ids, "
+                          "load_word_embeddings) do not need it") from e
+
+
+def _read_h5_splits(path, keys):
+    """``f[split][key][:]`` for the three splits (reference utils.py:35-49, 63-75, 106-120)."""
+    h5py = _h5py()
+    splits = ({}, {}, {})
+    with h5py.File(path, 'r') as f:
+        for k in keys:
+            for s, name in zip(splits, ('train', 'valid', 'test')):
+                s[k] = f[name][k][:]
+    return splits
+
+
+def load_word2ix(dataset, root='.'):
+    """token -> row index of the word table: the pickle of reference utils.py:21 (MOSI) or the JSON
+    mappings of utils.py:53 / 93 (POM, IEMOCAP)."""
+    import json
+    import os
+    import pickle
+    if dataset == 'mosi':
+        with open(os.path.join(root, 'mosi', 'word2ix_300_mosi.pkl'), 'rb') as fh:
+            return pickle.load(fh)
+    if dataset in ('pom', 'iemocap'):
+        with open(os.path.join(root, dataset, 'glove_mappings.%s.json' % dataset), 'r') as fh:
+            return json.load(fh)
+    raise ValueError('unknown dataset %r' % (dataset,))
+
+
+def load_word_embeddings(dataset, root='.'):
+    """The GloVe-300 table (reference utils.py:24 / 54 / 94)."""
+    import os
+    name = {'mosi': os.path.join('mosi', 'glove_300_mosi.npy'), 'pom': os.path.join('pom', 'glove.pom.npy'),
+            'iemocap': os.path.join('iemocap', 'glove.iemocap.npy')}
+    if dataset not in name:
+        raise ValueError('unknown dataset %r' % (dataset,))
+    return np.load(os.path.join(root, name[dataset]), allow_pickle=False)
+
+
+def load_text_ids(dataset, root='.', splits=('train', 'valid', 'test')):
+    """The right-padded (N, L) int64 id matrices of reference utils.py:82-88 / 122-128 (POM, IEMOCAP; MOSI
+    keeps its ids inside the h5 file).  Returns one array per requested split."""
+    import os
+    if dataset not in ('pom', 'iemocap'):
+        raise ValueError('%r has no separate id files' % (dataset,))
+    return [np.load(os.path.join(root, dataset, '%s_%s_ids.npy' % (dataset, s)), allow_pickle=False) for s in splits]
+
+
+def load_mosi(root='.'):
+    """reference utils.py:20-50."""
+    import os
+    word2ix = load_word2ix('mosi', root)
+    word_embeddings = load_word_embeddings('mosi', root)
+    splits = _read_h5_splits(os.path.join(root, 'data', 'mosi_data.h5'),
+                             ['facet', 'covarep', 'text', 'lengths', 'label', 'id'])
+    return word2ix, word_embeddings, splits
+
+
+def load_pom(root='.'):
+    """reference utils.py:52-90."""
+    import os
+    word2ix = load_word2ix('pom', root)
+    word_embeddings = load_word_embeddings('pom', root)
+    train, valid, test = _read_h5_splits(os.path.join(root, 'data', 'pom_data.h5'), ['facet', 'covarep', 'text', 'label'])
+    print(train['text'].shape)
+    train['text_id'], valid['text_id'], test['text_id'] = load_text_ids('pom', root)
+    print(train['text_id'].shape)
+    return word2ix, word_embeddings, (train, valid, test)
+
+
+def load_iemocap(args, root='.'):
+    """reference utils.py:92-128."""
+    import os
+    word2ix = load_word2ix('iemocap', root)
+    word_embeddings = load_word_embeddings('iemocap', root)
+    train, valid, test = _read_h5_splits(os.path.join(root, 'data', 'iemocap_{}.h5'.format(args['emotion'])),
+                                         ['facet', 'covarep', 'text', 'label'])
+    print(train['text'].shape)
+    train['text_id'], valid['text_id'], test['text_id'] = load_text_ids('iemocap', root)
+    return word2ix, word_embeddings, (train, valid, test)
+
+
+def load_data(args):
+    """reference utils.py:10-18 -- ``(word2ix, word_embeddings, (train, valid, test))`` from the reference's
+    file layout under the working directory (or ``args['data_root']``).  The files themselves are external
+    downloads (reference README.md:9, .MISSING_LARGE_BLOBS); a missing one raises FileNotFoundError."""
+    root = args.get('data_root', '.')
+    if args['dataset'] == 'mosi':
+        return load_mosi(root)
+    elif args['dataset'] == 'pom':
+        return load_pom(root)
+    elif args['dataset'] == 'iemocap':
+        return load_iemocap(args, root)
+    else:
+        raise ValueError
 
 
 def add_positional_embeddings(args, data):

@@ -253,3 +253,60 @@ def test_id_dataset_and_moment_batches_keep_the_reference_tuple_layout():
     assert len(xe) == 10 and isinstance(xe[8], losses.MomentStats) and xe[9] is None
     _, data, _ = simplesif._batch_dicts({'dataset': 'pom', 'unimodal': False}, xe, dse.table)
     assert isinstance(data['text'], losses.TokenIds) and isinstance(data['textaudio'].parts[0], losses.MomentStats)
+
+
+def test_loaders_read_the_reference_file_layout(tmp_path, monkeypatch):
+    """utils.load_data and its parts (reference utils.py:10-128): the id / vocabulary / table files by their
+    reference paths, the h5 splits through h5py (a stand-in module here: the image has no h5py)."""
+    import pickle
+    import sys
+    import types
+    import utils
+    root = tmp_path
+    (root / 'pom').mkdir()
+    (root / 'mosi').mkdir()
+    (root / 'data').mkdir()
+    rng = np.random.default_rng(0)
+    ids = {s: rng.integers(0, 50, size=(n, 9)).astype(np.int64) for s, n in (('train', 5), ('valid', 3), ('test', 4))}
+    for s, a in ids.items():
+        np.save(root / 'pom' / ('pom_%s_ids.npy' % s), a)
+    table = rng.standard_normal((50, 8)).astype(np.float32)
+    np.save(root / 'pom' / 'glove.pom.npy', table)
+    np.save(root / 'mosi' / 'glove_300_mosi.npy', table)
+    json.dump({'a': 1, '##b': 0}, open(root / 'pom' / 'glove_mappings.pom.json', 'w'))
+    pickle.dump({'the': 3}, open(root / 'mosi' / 'word2ix_300_mosi.pkl', 'wb'))
+    store = {}
+    for name in ('pom_data.h5', 'mosi_data.h5'):
+        store[str(root / 'data' / name)] = {
+            sp: {k: rng.standard_normal((n, 2)) for k in ('facet', 'covarep', 'text', 'label', 'lengths', 'id')}
+            for sp, n in (('train', 5), ('valid', 3), ('test', 4))}
+
+    class FakeFile(object):
+        def __init__(self, path, mode):
+            if path not in store:
+                raise FileNotFoundError(path)
+            self.d = store[path]
+
+        def __enter__(self):
+            return self.d
+
+        def __exit__(self, *a):
+            return False
+    monkeypatch.setitem(sys.modules, 'h5py', types.SimpleNamespace(File=FakeFile))
+    w2i, We, (tr, va, te) = utils.load_data({'dataset': 'pom', 'data_root': str(root)})
+    assert w2i == {'a': 1, '##b': 0}
+    np.testing.assert_array_equal(We, table)
+    np.testing.assert_array_equal(tr['text_id'], ids['train'])
+    np.testing.assert_array_equal(te['text_id'], ids['test'])
+    assert set(va) == {'facet', 'covarep', 'text', 'label', 'text_id'} and va['covarep'].shape == (3, 2)
+    w2i, We, (tr, va, te) = utils.load_data({'dataset': 'mosi', 'data_root': str(root)})
+    assert w2i == {'the': 3} and set(tr) == {'facet', 'covarep', 'text', 'lengths', 'label', 'id'}
+    with pytest.raises(ValueError):
+        utils.load_data({'dataset': 'nope'})
+    with pytest.raises(FileNotFoundError):
+        utils.load_data({'dataset': 'iemocap', 'emotion': 'happy', 'data_root': str(root)})
+    ref_root = '/root/reference'
+    if os.path.exists(os.path.join(ref_root, 'pom', 'pom_test_ids.npy')):       # the real fixtures, when present
+        v, t = utils.load_text_ids('pom', ref_root, ('valid', 'test'))
+        assert v.shape == (100, 1089) and t.shape == (203, 1357) and t.dtype == np.int64
+        assert max(utils.load_word2ix('mosi', ref_root).values()) == 3015

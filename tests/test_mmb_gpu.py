@@ -458,3 +458,46 @@ def test_downstream_metrics(mods, golden_dir, tag, graph, text_ids, capsys):
             got, want = np.asarray(results[k], dtype=np.float64), g['%s_after_%s' % (tag, k)]
             tol = 0.03 if k == 'f_score' else 1.5 / len(splits[2]['label'])
             assert np.abs(got - want).max() <= tol, (k, got, want)
+
+
+@pytest.mark.parametrize('config_num', [5, 302])
+def test_sweep_grid_point_equals_run_experiment(mods, config_num, capsys):
+    """BASELINE config 5 (the reference grid, configs/make_configs.py:16-32): one grid point through
+    ``sweep.run_config`` -- shared SIF initialisation and device datasets, per-config seed, graph replay --
+    gives the metrics of ``simplesif.run_experiment`` (everything the reference's main() does after loading)
+    on the same splits under the same seed.  config 5: layer_norm + adam; 302: batch_norm + sgd."""
+    torch = mods[0]
+    import copy
+    import simplesif
+    import sweep
+    import utils
+    grid = sweep.make_grid()
+    assert len(grid) == 512 and grid[config_num]['config_num'] == config_num
+    cfg = grid[config_num]
+    dev = torch.device('cuda')
+    We, weights, splits = sweep.synthetic_mosi(seed=3, sizes=(200, 60, 90), V=400)
+    scale = 0.04                                     # 4 / 8 latent epochs, 16 regressor epochs
+    prep = sweep.Prepared(We, weights, copy.deepcopy(splits), dev)
+    got = sweep.run_config(cfg, prep, epochs_scale=scale)
+    capsys.readouterr()
+    # the same grid point the long way round
+    args = {'dataset': 'mosi', 'unimodal': False, 'early_stopping': False, 'lr_decay': 0.5, 'cuda_graph': 1,
+            'batch_size': 64, 'n_runs': 1}
+    args.update(cfg)
+    args['n_epochs'] = max(1, int(round(cfg['n_epochs'] * scale)))
+    args['n_sentiment_epochs'] = max(1, int(round(cfg['n_sentiment_epochs'] * scale)))
+    raw, masks = [], []
+    for s in copy.deepcopy(splits):
+        s, m = utils.normalize_data(s)
+        simplesif.update_masks(m, s['text'], We.shape[-1])
+        raw.append(s)
+        masks.append(m)
+    torch.manual_seed(1000 + config_num)
+    (results, train_losses, _), = simplesif.run_experiment(args, We, weights, raw, masks, dev)
+    capsys.readouterr()
+    if got.get('diverged'):
+        pytest.skip('config diverges on this synthetic data: %s' % got.get('message'))
+    assert abs(got['train_loss'] - train_losses[-1]) <= 1e-6 * abs(train_losses[-1])
+    for k in ('mae', 'corr', 'accuracy', 'mult_acc', 'f_score'):
+        np.testing.assert_allclose(np.asarray(got['results'][k], dtype=np.float64),
+                                   np.asarray(results[k], dtype=np.float64), rtol=0, atol=1e-6, err_msg=k)

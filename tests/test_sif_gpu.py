@@ -423,3 +423,86 @@ def test_fused_lookup_equals_explicit_weights_large(mods, V, d, L):
     nv.check(lib.mmb_sif_embed(nv.ptr(t_We), V, d, nv.ptr(t_vw), nv.ptr(t_ids), n, L, nv.ptr(hot), nv.ptr(st),
                                nv.stream_ptr()))
     assert int(st.item()) & nv.STATUS_BAD_INDEX
+
+
+# --------------------------------------------------------------------------------------------------
+# ragged (CSR) ids, device-side masks
+
+@pytest.mark.parametrize('split', ['valid', 'test'])
+def test_ragged_ids_equal_padded_reference_pom(mods, golden_dir, split):
+    """The real POM splits (73 % padding, pad id 0 with weight 1.0) as CSR ids: same embeddings as the
+    reference computed on the padded matrix -- the pad run is added in closed form, the divisor still counts it."""
+    import torch
+    nv, sf, sif = mods
+    g = np.load(os.path.join(golden_dir, 'sif_pom_full.npz'))
+    ids = g[split + '_ids'].astype(np.int64)
+    We = cases.table(7763, 300, seed=11)
+    rag = sf.to_ragged(ids)
+    lens = rag.lengths().cpu().numpy()
+    want_lens = np.array([np.max(np.nonzero(r)[0]) + 1 if r.any() else 0 for r in ids])
+    np.testing.assert_array_equal(lens, want_lens)                              # offsets: bit-exact
+    np.testing.assert_array_equal(rag.to_padded().cpu().numpy(), ids)           # lossless round trip
+    assert int(rag.tokens.numel()) == int(want_lens.sum()) < ids.size // 2
+    dev = torch.device('cuda')
+    t_We = torch.tensor(We, device=dev)
+    t_w = torch.tensor(g['weights'].astype(np.float32), device=dev)
+    avg = sf.sif_embedding_ragged(t_We, t_w, rag, npc=0)
+    assert rel_err(avg.double().cpu().numpy(), g[split + '_avg'].astype(np.float64)) < EMB_RTOL
+    emb = sif.get_sentence_embeddings(We, g['weights'], rag)                    # the drop-in call takes RaggedIds
+    assert rel_err(emb.double().cpu().numpy(), g[split + '_emb'].astype(np.float64)) < EMB_RTOL
+
+
+@pytest.mark.parametrize('n,L,V,d,w0', [(300, 64, 900, 300, 1.0), (77, 33, 50, 128, 0.0), (5000, 64, 4000, 300, 0.25),
+                                        (9, 1, 7, 64, 1.0), (40, 200, 30, 512, 1.0)])
+def test_ragged_ids_vs_oracle(mods, n, L, V, d, w0):
+    """Ragged ids against the NumPy oracle on the padded matrix: pad weight 1 / 0 / fractional, interior pad
+    ids (the shared OOV row), empty utterances (all pad -> the divisor is L or 0 -> NaN as in NumPy)."""
+    import torch
+    nv, sf, sif = mods
+    rng = np.random.default_rng(n + L)
+    We = cases.table(V, d, seed=n)
+    ids, p = cases.zipf_ids(rng, n, L, V)
+    ids[rng.random(ids.shape) < 0.05] = 0            # interior zeros
+    if n > 3:
+        ids[2] = 0                                   # an utterance that is all padding
+    weights = cases.sif_weights(p)
+    weights[0] = w0
+    w = so.seq2weight(ids, np.ones(ids.shape), weights)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        want = so.get_weighted_average(We, ids, w)
+    dev = torch.device('cuda')
+    rag = sf.to_ragged(ids)
+    np.testing.assert_array_equal(rag.to_padded().cpu().numpy(), ids)
+    got = sf.sif_embedding_ragged(torch.tensor(We, device=dev), torch.tensor(weights.astype(np.float32), device=dev),
+                                  rag, npc=0).double().cpu().numpy()
+    dead = ~np.isfinite(want).all(axis=1)
+    assert np.array_equal(dead, ~np.isfinite(got).all(axis=1))
+    assert rel_err(got[~dead], want[~dead]) < EMB_RTOL
+    # and the full pipeline equals the padded device call
+    if n >= 300:
+        a = sf.sif_embedding_ragged(torch.tensor(We, device=dev), torch.tensor(weights.astype(np.float32), device=dev),
+                                    rag, npc=1)
+        b = sf.sif_embedding_device(torch.tensor(We, device=dev), torch.tensor(weights.astype(np.float32), device=dev),
+                                    torch.tensor(ids, device=dev), npc=1)
+        ok = torch.isfinite(b).all(dim=1)
+        assert rel_err(a[ok].double().cpu().numpy(), b[ok].double().cpu().numpy()) < EMB_RTOL
+
+
+def test_device_masks_equal_reference_masks(mods, capsys):
+    """update_masks / update_masks_vect (reference simplesif.py:36-47) on the device."""
+    import torch
+    import simplesif
+    rng = np.random.default_rng(4)
+    ids = rng.integers(0, 5, size=(37, 21)).astype(np.int64)
+    m_ref, m_dev = {}, {}
+    simplesif.update_masks(m_ref, ids, 12)
+    simplesif.update_masks_device(m_dev, ids, 12)
+    assert tuple(m_dev['text'].shape) == m_ref['text'].shape and m_dev['text'].stride(-1) == 0
+    np.testing.assert_array_equal(m_dev['text'].cpu().numpy(), m_ref['text'].astype(np.float32))
+    x = rng.standard_normal((19, 23, 45)).astype(np.float32)
+    x[rng.random(x.shape) < 0.01] = 0.0
+    x[:, 20:, :] = 0.0
+    simplesif.update_masks_vect(m_ref, x, 'text_align')
+    simplesif.update_masks_vect_device(m_dev, x, 'text_align')
+    np.testing.assert_array_equal(m_dev['text_align'].cpu().numpy(), m_ref['text_align'].astype(np.float32))
+    capsys.readouterr()
