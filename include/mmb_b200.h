@@ -94,6 +94,16 @@ MMB_API int mmb_weighted_average(const float* table, int64_t V, int d, const int
 MMB_API int mmb_sif_embed(const float* table, int64_t V, int d, const float* vocab_w, const int64_t* x,
                   int64_t N, int64_t L, float* emb, int* status, mmb_stream_t stream);
 
+/* mmb_sif_embed with scratch: for large batches (N * L >= 8 V) the vocabulary weights are folded into a
+ * scratch copy of the table once per call (T' = w * T), after which a token costs one row read and one warp
+ * shuffle -- no weight gather.  Same result up to one rounding per term (w * row rounded before the sum).
+ * mmb_sif_embed_workspace_bytes returns 0 when the plain kernel is the right one (small batch, few long
+ * rows, d > 512, table >= 4 GiB); with ws == NULL or too small the call IS mmb_sif_embed.              */
+MMB_API size_t mmb_sif_embed_workspace_bytes(int64_t V, int d, int64_t N, int64_t L);
+MMB_API int mmb_sif_embed_ws(const float* table, int64_t V, int d, const float* vocab_w, const int64_t* x,
+                             int64_t N, int64_t L, float* emb, int* status, void* ws, size_t ws_bytes,
+                             mmb_stream_t stream);
+
 /* Ragged (CSR) ids, SURVEY.md 8f N3 -- the same result as mmb_sif_embed on the right-padded (N, L_pad)
  * matrix the reference builds (utils.py:77-80; sif_functions.py:28-56), without walking the padding:
  * utterance i is tokens[offsets[i] .. offsets[i+1]) (int64, offsets has N + 1 entries) and is understood

@@ -138,6 +138,12 @@ extern "C" int mmb_gram(const float* X, int64_t N, int d, float* G, void* ws, si
 }
 
 // ---- composed pipeline, everything resident on the device ---------------------------------
+namespace mmb {   // implemented in sif_embed.cu
+int sif_prescale(const float* table, int64_t V, int d, const float* vocab_w, void* ws, cudaStream_t st);
+int sif_embed_prescaled(const float* table, int64_t V, int d, const float* vocab_w, const void* ws, const int64_t* x,
+                        int64_t N, int64_t L, float* emb, int* status, cudaStream_t st);
+}  // namespace mmb
+
 struct SifWs {
   size_t gram, pc, s0, G, pcv, total;
 };
@@ -187,7 +193,15 @@ extern "C" int mmb_sif_embedding(const float* table, int64_t V, int d, const flo
                                  const int64_t* x, int64_t N, int64_t L, int npc, const double* Omega,
                                  float* emb, float* pc, float* G, void* ws, size_t ws_bytes,
                                  int gram_mode, int* status, mmb_stream_t stream) {
-  int rc = mmb_sif_embed(table, V, d, vocab_w, x, N, L, emb, status, stream);
+  // scratch for the pre-scaled table (large batches) sits behind the Gram / solve workspace when the caller
+  // provided mmb_sif_workspace_bytes(N, d, npc) + mmb_sif_embed_workspace_bytes(V, d, N, L) bytes
+  const size_t base_bytes = align_up(mmb_sif_workspace_bytes(N > 0 ? N : 1, d, npc));
+  const size_t scaled_bytes = mmb_sif_embed_workspace_bytes(V, d, N, L);
+  int rc;
+  if (scaled_bytes && ws && ws_bytes >= base_bytes + scaled_bytes)
+    rc = mmb_sif_embed_ws(table, V, d, vocab_w, x, N, L, emb, status, (char*)ws + base_bytes, scaled_bytes, stream);
+  else
+    rc = mmb_sif_embed(table, V, d, vocab_w, x, N, L, emb, status, stream);
   if (rc || npc <= 0 || N == 0) return rc;
   return pc_removal_device(emb, N, d, npc, Omega, pc, G, ws, ws_bytes, gram_mode, as_stream(stream));
 }
@@ -311,7 +325,7 @@ static int sif_embedding_host_impl(const float* table_dev, int64_t V, int d, con
   Streams S;
   int rc = S.init();
   if (rc) return rc;
-  DevBuf ids[2], emb, ws, omega, status, pcv, f64[2], gchunk;
+  DevBuf ids[2], emb, ws, omega, status, pcv, f64[2], gchunk, scaled;
   SyncGuard sync_guard{S};
   AbortGuard abort_guard{hc, S.comp, dist && npc > 0};
   const bool chunked_gram = npc > 0 && nchunks > 1;
@@ -336,6 +350,12 @@ static int sif_embedding_host_impl(const float* table_dev, int64_t V, int d, con
     if ((rc = f64[0].alloc(b, S.comp))) return rc;
     if ((rc = f64[1].alloc(b, S.comp))) return rc;
   }
+  // large batches: weights folded into the table once (sif_embed.cu); decided on the WHOLE batch, not per chunk
+  const size_t scaled_bytes = mmb_sif_embed_workspace_bytes(V, d, N, L);
+  if (scaled_bytes) {
+    if ((rc = scaled.alloc(scaled_bytes, S.comp))) return rc;
+    if ((rc = sif_prescale(table_dev, V, d, vocab_w_dev, scaled.p, S.comp))) return rc;
+  }
   cudaEvent_t allocs_done;
   if ((rc = S.event(&allocs_done))) return rc;
   MMB_CUDA(cudaEventRecord(allocs_done, S.comp));
@@ -357,8 +377,12 @@ static int sif_embedding_host_impl(const float* table_dev, int64_t V, int d, con
                              cudaMemcpyHostToDevice, S.in));
     MMB_CUDA(cudaEventRecord(in_ready[b], S.in));
     MMB_CUDA(cudaStreamWaitEvent(S.comp, in_ready[b], 0));
-    rc = mmb_sif_embed(table_dev, V, d, vocab_w_dev, (const int64_t*)ids[b].p, rows, L,
-                       (float*)emb.p + r0 * d, (int*)status.p, S.comp);
+    if (scaled_bytes)
+      rc = sif_embed_prescaled(table_dev, V, d, vocab_w_dev, scaled.p, (const int64_t*)ids[b].p, rows, L,
+                               (float*)emb.p + r0 * d, (int*)status.p, S.comp);
+    else
+      rc = mmb_sif_embed(table_dev, V, d, vocab_w_dev, (const int64_t*)ids[b].p, rows, L,
+                         (float*)emb.p + r0 * d, (int*)status.p, S.comp);
     if (rc) return rc;
     MMB_CUDA(cudaEventRecord(buf_free[b], S.comp));
     if (chunked_gram) {

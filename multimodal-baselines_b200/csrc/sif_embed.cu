@@ -252,7 +252,10 @@ template <int NCH, int UNROLL, int MINB>
 __global__ void __launch_bounds__(kEmbedWarps * 32, MINB)
     sif_embed_warp_prefetch_kernel(const float4* __restrict__ table4, int V, int d4, const float* __restrict__ wsrc,
                                    const int64_t* __restrict__ ids, int64_t N, int64_t L,
-                                   float4* __restrict__ emb4, int* __restrict__ status) {
+                                   float4* __restrict__ emb4, int* __restrict__ status,
+                                   const int* __restrict__ only_if_flag = nullptr) {
+  // launched behind sif_embed_prescaled_kernel: work only if that one stood down (flag bit 0 set)
+  if (only_if_flag && !(__ldg(only_if_flag) & 1)) return;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kEmbedWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kEmbedWarps;
@@ -303,6 +306,116 @@ __global__ void __launch_bounds__(kEmbedWarps * 32, MINB)
     for (int64_t base = 0; base < L; base += 32)
       cnt += accumulate_chunk<NCH, EXPLICIT_W, UNROLL, WIDE>(acc, lane_base, V, row_bytes, tail, wsrc, row_ids,
                                                              row_w, base, L, lane, bad);
+    store_row<NCH>(emb4 + (size_t)i * d4, acc, cnt, lane, d4);
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, MMB_STATUS_BAD_INDEX);
+}
+
+// ---- large batches: table pre-scaled by the vocabulary weights -------------------------------------------
+// For N * L >> V the weights are folded into the table once per call: T'[v] = w[v] * T[v] (one streaming pass
+// over the table, 2 * V * d * 4 bytes), after which a token contributes the ROW T'[id] and nothing else:
+//   * no weight gather (a random 4-byte read per token = one 32-byte sector through L2 -> L1 and up to 32
+//     L1 wavefronts per 32-token chunk),
+//   * ONE warp shuffle per gathered row instead of two (row index and multiplicity packed in one word; the
+//     shuffles share the L1 data pipe with the row loads -- 20 % of its wavefronts in the general kernel),
+//   * a merged group's multiplier is popc(match mask), no reduction loop.
+// The divisor needs "weight != 0" per token: the pre-scale pass raises flag bit 0 if ANY vocabulary weight is
+// zero (SIF weights a / (a + p) never are); the kernel then returns at once and the general kernel, launched
+// behind it, does the work (and returns at once in the usual case) -- no host round trip.  Negative ids keep
+// NumPy's semantics: the wrapped row is read and multiplied by 0, and does not count in the divisor.
+// Rounding: w * row is rounded once before the sum instead of fused into it -- 2^-24 per term, inside the
+// 1e-5 embedding tolerance; the order of the sum is fixed, so the result is deterministic.
+constexpr int kRowBits = 26;   // row index below 2^26 (V < 67 M), multiplicity (<= 32) above
+
+__global__ void __launch_bounds__(256)
+    prescale_table_kernel(const float4* __restrict__ table4, const float* __restrict__ w, int V, int d4,
+                          float4* __restrict__ out4, int* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  bool zero = false;
+  for (int64_t v = warp0; v < V; v += nwarps) {
+    const float wv = __ldg(w + v);
+    zero = zero || (wv == 0.f);
+    for (int k = lane; k < d4; k += 32) {
+      float4 r = ld_stream(table4 + v * d4 + k);
+      r.x *= wv; r.y *= wv; r.z *= wv; r.w *= wv;
+      out4[v * d4 + k] = r;            // plain store: the rows are about to be gathered (keep them in L2)
+    }
+  }
+  if (zero && lane == 0) atomicOr(flags, 1);
+}
+
+template <int NCH, int UNROLL, int MINB>
+__global__ void __launch_bounds__(kEmbedWarps * 32, MINB)
+    sif_embed_prescaled_kernel(const float4* __restrict__ tp4, int V, int d4, const int* __restrict__ flags,
+                               const int64_t* __restrict__ ids, int64_t N, int64_t L, float4* __restrict__ emb4,
+                               int* __restrict__ status) {
+  if (__ldg(flags) & 1) return;        // a zero vocabulary weight: the general kernel behind this one runs
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kEmbedWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kEmbedWarps;
+  const char* lane_base = (const char*)(tp4 + lane);
+  const unsigned row_bytes = (unsigned)d4 * 16u;
+  const typename Live<NCH>::type tail = make_live<NCH>(lane, d4);
+  bool bad = false;
+  int64_t nid = (warp0 < N && lane < L) ? __ldcs(ids + warp0 * L + lane) : 0;
+  for (int64_t i = warp0; i < N; i += nwarps) {
+    RowAcc<NCH> acc;
+    acc.clear();
+    int cnt = 0;
+    for (int64_t base = 0; base < L; base += 32) {
+      const int64_t id = nid;
+      const bool same = base + 32 < L;
+      const int64_t ni = same ? i : i + nwarps;
+      const int64_t nb = same ? base + 32 : 0;
+      nid = (ni < N && nb + lane < L) ? __ldcs(ids + ni * L + nb + lane) : 0;      // next chunk's ids in flight
+      int row = -1;
+      bool counts = false;
+      if (base + lane < L) {
+        const int64_t r = id < 0 ? id + V : id;
+        if (r >= 0 && r < V) {
+          row = (int)r;
+          counts = id >= 0;            // seq2weight: negative ids get weight 0
+        } else {
+          bad = true;                  // NumPy: IndexError
+        }
+      }
+      const unsigned nn = __ballot_sync(0xffffffffu, counts);
+      cnt += __popc(nn);
+      const unsigned grp = __match_any_sync(0xffffffffu, row);
+      const bool head = (row >= 0) && (lane == __ffs(grp) - 1);
+      const unsigned packed = (unsigned)row | ((unsigned)__popc(grp & nn) << kRowBits);
+      unsigned heads = __ballot_sync(0xffffffffu, head);
+      while (heads) {
+        int j[UNROLL];
+        int n = 0;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          j[u] = heads ? (__ffs(heads) - 1) : 0;
+          if (heads) { heads &= heads - 1; ++n; }
+        }
+        if (n == UNROLL) {
+          float mj[UNROLL];
+          float4 v[UNROLL][NCH];
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u) {
+            const unsigned pj = __shfl_sync(0xffffffffu, packed, j[u]);
+            mj[u] = (float)(pj >> kRowBits);
+            load_row<NCH>(v[u], lane_base, (pj & ((1u << kRowBits) - 1u)) * row_bytes, tail);
+          }
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u) fma_row<NCH>(acc, v[u], mj[u], tail);
+        } else {
+          for (int u = 0; u < n; ++u) {
+            const unsigned pj = __shfl_sync(0xffffffffu, packed, j[u]);
+            float4 vv[NCH];
+            load_row<NCH>(vv, lane_base, (pj & ((1u << kRowBits) - 1u)) * row_bytes, tail);
+            fma_row<NCH>(acc, vv, (float)(pj >> kRowBits), tail);
+          }
+        }
+      }
+    }
     store_row<NCH>(emb4 + (size_t)i * d4, acc, cnt, lane, d4);
   }
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, MMB_STATUS_BAD_INDEX);
@@ -675,4 +788,80 @@ extern "C" int mmb_ids_compact(const int64_t* ids, int64_t N, int64_t L, const i
   ids_compact_kernel<<<grid, 256, 0, as_stream(stream)>>>(ids, N, L, offsets, tokens);
   MMB_LAUNCH_CHECK("ids_compact");
   return MMB_OK;
+}
+
+extern "C" size_t mmb_sif_embed_workspace_bytes(int64_t V, int d, int64_t N, int64_t L) {
+  // pre-scaled table + flag word; 0 = the batch is too small for the pre-scale pass to pay (or out of range)
+  static const bool off = getenv("MMB_EMBED_PRESCALE") && atoi(getenv("MMB_EMBED_PRESCALE")) == 0;
+  if (off || d <= 0 || d % 4 != 0 || d > 512 || V <= 0 || V >= ((int64_t)1 << kRowBits)) return 0;
+  if ((uint64_t)V * (uint64_t)d * 4u >= ((uint64_t)1 << 32)) return 0;
+  if (L >= 256 && N < (int64_t)sm_count() * 16) return 0;     // few long rows: the CTA-per-utterance kernel
+  if (N * L < 8 * V) return 0;
+  return (size_t)V * d * sizeof(float) + 256;
+}
+
+namespace mmb {
+// T' = w * T into ws (+ the zero-weight flag); once per (table, weights), i.e. once per call.
+int sif_prescale(const float* table, int64_t V, int d, const float* vocab_w, void* ws, cudaStream_t st) {
+  int* flags = (int*)ws;
+  float4* tp4 = (float4*)((char*)ws + 256);
+  MMB_CUDA(cudaMemsetAsync(flags, 0, sizeof(int), st));
+  prescale_table_kernel<<<sm_count() * 8, 256, 0, st>>>((const float4*)table, vocab_w, (int)V, d / 4, tp4, flags);
+  MMB_LAUNCH_CHECK("prescale_table");
+  return MMB_OK;
+}
+
+// The embed pass on a pre-scaled table (ws from sif_prescale) with the general kernel standing by.
+int sif_embed_prescaled(const float* table, int64_t V, int d, const float* vocab_w, const void* ws, const int64_t* x,
+                        int64_t N, int64_t L, float* emb, int* status, cudaStream_t st) {
+  if (N == 0) return MMB_OK;
+  const int d4 = d / 4;
+  const int* flags = (const int*)ws;
+  const float4* tp4 = (const float4*)((const char*)ws + 256);
+  const int sms = sm_count();
+  const int64_t blocks = ceil_div(N, kEmbedWarps);
+  const int grid = (int)(blocks < (int64_t)sms * 8 ? blocks : (int64_t)sms * 8);
+  static const int variant = getenv("MMB_EMBED_PS_VARIANT") ? atoi(getenv("MMB_EMBED_PS_VARIANT")) : 0;
+#define PS_KERNEL(NCH, U, B)                                                                                   \
+  sif_embed_prescaled_kernel<NCH, U, B><<<grid, kEmbedWarps * 32, 0, st>>>(tp4, (int)V, d4, flags, x, N, L,    \
+                                                                           (float4*)emb, status)
+#define PRESCALED_LAUNCH(NCH)                                                                                  \
+  do {                                                                                                         \
+    if (variant == 1) PS_KERNEL(NCH, 3, 4);                                                                    \
+    else if (variant == 2) PS_KERNEL(NCH, 3, 3);                                                               \
+    else if (variant == 3) PS_KERNEL(NCH, 4, 3);                                                               \
+    else PS_KERNEL(NCH, 2, 4);                                                                                 \
+    MMB_LAUNCH_CHECK("sif_embed_prescaled");                                                                   \
+    sif_embed_warp_prefetch_kernel<NCH, 2, 4><<<grid, kEmbedWarps * 32, 0, st>>>(                              \
+        (const float4*)table, (int)V, d4, vocab_w, x, N, L, (float4*)emb, status, flags);                      \
+    MMB_LAUNCH_CHECK("sif_embed_general_standby");                                                             \
+    note_kernel(0, variant == 1 ? "sif_embed_prescaled_kernel<" #NCH ",3,4>"                                  \
+                   : variant == 2 ? "sif_embed_prescaled_kernel<" #NCH ",3,3>"                                \
+                   : variant == 3 ? "sif_embed_prescaled_kernel<" #NCH ",4,3>"                                \
+                                  : "sif_embed_prescaled_kernel<" #NCH ",2,4>");                              \
+  } while (0)
+  switch ((d4 + 31) / 32) {
+    case 1: PRESCALED_LAUNCH(1); break;
+    case 2: PRESCALED_LAUNCH(2); break;
+    case 3: PRESCALED_LAUNCH(3); break;
+    default: PRESCALED_LAUNCH(4); break;
+  }
+#undef PRESCALED_LAUNCH
+#undef PS_KERNEL
+  return MMB_OK;
+}
+}  // namespace mmb
+
+extern "C" int mmb_sif_embed_ws(const float* table, int64_t V, int d, const float* vocab_w, const int64_t* x,
+                                int64_t N, int64_t L, float* emb, int* status, void* ws, size_t ws_bytes,
+                                mmb_stream_t stream) {
+  const size_t need = mmb_sif_embed_workspace_bytes(V, d, N, L);
+  if (need == 0 || ws == nullptr || ws_bytes < need || N == 0)
+    return mmb_sif_embed(table, V, d, vocab_w, x, N, L, emb, status, stream);
+  MMB_REQUIRE(table && vocab_w && x && emb && status, "null pointer");
+  MMB_REQUIRE(((uintptr_t)table % 16 == 0) && ((uintptr_t)emb % 16 == 0) && ((uintptr_t)ws % 16 == 0),
+              "table / emb / ws must be 16-byte aligned");
+  int rc = sif_prescale(table, V, d, vocab_w, ws, as_stream(stream));
+  if (rc) return rc;
+  return sif_embed_prescaled(table, V, d, vocab_w, ws, x, N, L, emb, status, as_stream(stream));
 }

@@ -257,6 +257,19 @@ def local_start_block(emb_local, n_global, lo, npc, start_block_fn):
     return S0
 
 
+_EMBED_SCRATCH = {}
+
+
+def _embed_scratch(nbytes, dev):
+    """One scratch buffer per device for the pre-scaled table of mmb_sif_embed_ws (reused across calls: the
+    same stream orders its uses)."""
+    t = _EMBED_SCRATCH.get(str(dev))
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _EMBED_SCRATCH[str(dev)] = t
+    return t
+
+
 def sharded_sif_embedding(table_t, vocab_w_t, ids_local_t, n_global, lo, npc=1, group=None, gram_mode=0,
                           timers=None, comm='auto'):
     """SIF embedding + PC removal of this rank's block of a split of `n_global` utterances.
@@ -275,8 +288,10 @@ def sharded_sif_embedding(table_t, vocab_w_t, ids_local_t, n_global, lo, npc=1, 
     dev = table_t.device
     emb = torch.empty((n_local, d), dtype=torch.float32, device=dev)
     st = torch.zeros(1, dtype=torch.int32, device=dev)
-    nv.check(lib.mmb_sif_embed(nv.ptr(table_t), V, d, nv.ptr(vocab_w_t), nv.ptr(ids_local_t), n_local, L,
-                               nv.ptr(emb), nv.ptr(st), nv.stream_ptr()))
+    ws_bytes = lib.mmb_sif_embed_workspace_bytes(V, d, n_local, L)   # > 0: large batch, weights folded into a scratch table
+    ws = _embed_scratch(ws_bytes, dev) if ws_bytes else None
+    nv.check(lib.mmb_sif_embed_ws(nv.ptr(table_t), V, d, nv.ptr(vocab_w_t), nv.ptr(ids_local_t), n_local, L,
+                                  nv.ptr(emb), nv.ptr(st), nv.ptr(ws), ws_bytes, nv.stream_ptr()))
     mark('embed')
     if npc <= 0:
         return emb, None, st

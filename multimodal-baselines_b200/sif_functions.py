@@ -229,6 +229,9 @@ def sif_embedding_device(table_t, vocab_w_t, ids_t, npc=1, gram_mode=nv.GRAM_AUT
     if npc > 0 and omega_t is None:
         omega_t = start_block_device(d if n >= d else n, npc, dev)
     nbytes = lib.mmb_sif_workspace_bytes(n, d, npc)
+    extra = lib.mmb_sif_embed_workspace_bytes(V, d, n, L)     # large batches: scratch for the pre-scaled table
+    if extra:
+        nbytes = (nbytes + 255) // 256 * 256 + extra
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     nv.check(lib.mmb_sif_embedding(nv.ptr(table_t), V, d, nv.ptr(vocab_w_t), nv.ptr(ids_t), n, L, npc,
                                    nv.ptr(omega_t), nv.ptr(emb), nv.ptr(pc), None, nv.ptr(ws), nbytes,

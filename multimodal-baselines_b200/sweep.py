@@ -203,11 +203,16 @@ def main(argv=None):
     local = int(os.environ.get('LOCAL_RANK', 0))
     if not torch.cuda.is_available():
         raise RuntimeError('sweep.py runs on CUDA devices only (no CPU fallback)')
+    # More ranks than GPUs is allowed and useful: rank r runs on GPU r % n_gpus, so K = world / n_gpus
+    # processes share each GPU.  One config keeps a B200 busy for a fraction of the time (B = 64 kernels
+    # between graph captures and host-side bookkeeping); K processes fill each other's gaps.
+    n_dev = torch.cuda.device_count()
+    local = local % n_dev
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=device)
+        dist.init_process_group('gloo')          # results are gathered as Python objects; no GPU collective
     warnings.filterwarnings('ignore', message='.*ill-defined.*')   # sklearn's report on empty classes
     grid = make_grid()
     if a.limit:
@@ -243,7 +248,9 @@ def main(argv=None):
                     f.write(json.dumps(r) + '\n')
         maes = [r['results']['mae'] for r in out if 'results' in r]
         print(json.dumps({'metric': 'grid configs/s (e2e train + valid/test latents + sentiment regressor)',
-                          'configs': len(out), 'n_gpus': world, 'seconds': dt, 'value': len(out) / dt,
+                          'configs': len(out), 'n_gpus': min(world, n_dev), 'processes': world,
+                          'processes_per_gpu': max(1, world // max(n_dev, 1)), 'seconds': dt, 'value': len(out) / dt,
+                          'value_per_gpu': len(out) / dt / max(1, min(world, n_dev)),
                           'epochs_scale': a.epochs_scale, 'cuda_graph': not a.no_graph,
                           'diverged': [r['config_num'] for r in out if r.get('diverged')],
                           'best_test_MAE': (min(maes) if maes else None)}), flush=True)

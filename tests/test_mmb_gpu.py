@@ -460,12 +460,14 @@ def test_downstream_metrics(mods, golden_dir, tag, graph, text_ids, capsys):
             assert np.abs(got - want).max() <= tol, (k, got, want)
 
 
-@pytest.mark.parametrize('config_num', [5, 302])
+@pytest.mark.parametrize('config_num', [5, 303, 302])
 def test_sweep_grid_point_equals_run_experiment(mods, config_num, capsys):
     """BASELINE config 5 (the reference grid, configs/make_configs.py:16-32): one grid point through
     ``sweep.run_config`` -- shared SIF initialisation and device datasets, per-config seed, graph replay --
     gives the metrics of ``simplesif.run_experiment`` (everything the reference's main() does after loading)
-    on the same splits under the same seed.  config 5: layer_norm + adam; 302: batch_norm + sgd."""
+    on the same splits under the same seed.  config 5: layer_norm + adam; 303: batch_norm + adam; 302:
+    batch_norm + sgd, which diverges on the synthetic data -- then BOTH must end in the reference's sys.exit()
+    (losses.py:258-264), which the sweep reports as `diverged`."""
     torch = mods[0]
     import copy
     import simplesif
@@ -493,10 +495,13 @@ def test_sweep_grid_point_equals_run_experiment(mods, config_num, capsys):
         raw.append(s)
         masks.append(m)
     torch.manual_seed(1000 + config_num)
+    if got.get('diverged'):
+        with pytest.raises(SystemExit):
+            simplesif.run_experiment(args, We, weights, raw, masks, dev)
+        capsys.readouterr()
+        return
     (results, train_losses, _), = simplesif.run_experiment(args, We, weights, raw, masks, dev)
     capsys.readouterr()
-    if got.get('diverged'):
-        pytest.skip('config diverges on this synthetic data: %s' % got.get('message'))
     assert abs(got['train_loss'] - train_losses[-1]) <= 1e-6 * abs(train_losses[-1])
     for k in ('mae', 'corr', 'accuracy', 'mult_acc', 'f_score'):
         np.testing.assert_allclose(np.asarray(got['results'][k], dtype=np.float64),

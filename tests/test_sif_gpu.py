@@ -506,3 +506,58 @@ def test_device_masks_equal_reference_masks(mods, capsys):
     simplesif.update_masks_vect_device(m_dev, x, 'text_align')
     np.testing.assert_array_equal(m_dev['text_align'].cpu().numpy(), m_ref['text_align'].astype(np.float32))
     capsys.readouterr()
+
+
+def test_prescaled_table_path_equals_general_kernel(mods):
+    """Large batches fold the vocabulary weights into a scratch copy of the table (mmb_sif_embed_ws): same
+    averages as the general kernel and the oracle (one extra rounding per term); a zero vocabulary weight
+    hands the batch to the general kernel (the divisor must not count that token); negative ids wrap like
+    NumPy and do not count; an out-of-range id still raises."""
+    import torch
+    nv, sf, sif = mods
+    lib = nv.lib
+    dev = torch.device('cuda')
+    rng = np.random.default_rng(12)
+    V, d, n, L = 2000, 300, 4000, 64                      # N * L = 256,000 >= 8 V
+    We = cases.table(V, d, seed=3)
+    ids, p = cases.zipf_ids(rng, n, L, V)
+    ids[5, 3] = -7                                         # NumPy: row V - 7, weight 0
+    weights = cases.sif_weights(p).astype(np.float32)
+    t_We, t_ids = torch.tensor(We, device=dev), torch.tensor(ids, device=dev)
+
+    def run(w_np, ids_t, use_ws):
+        t_w = torch.tensor(w_np, device=dev)
+        emb = torch.empty((ids_t.shape[0], d), dtype=torch.float32, device=dev)
+        st = torch.zeros(1, dtype=torch.int32, device=dev)
+        nbytes = lib.mmb_sif_embed_workspace_bytes(V, d, ids_t.shape[0], L) if use_ws else 0
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        nv.check(lib.mmb_sif_embed_ws(nv.ptr(t_We), V, d, nv.ptr(t_w), nv.ptr(ids_t), ids_t.shape[0], L, nv.ptr(emb),
+                                      nv.ptr(st), nv.ptr(ws) if use_ws else None, nbytes, nv.stream_ptr()))
+        return emb, int(st.item()), nbytes, (lib.mmb_last_kernel(0) or b'').decode()
+
+    fast, st, nbytes, kname = run(weights, t_ids, True)
+    assert nbytes >= V * d * 4 and st == 0 and 'prescaled' in kname
+    plain, st2, _, kname2 = run(weights, t_ids, False)
+    assert st2 == 0 and 'prescaled' not in kname2
+    w = so.seq2weight(ids, np.ones(ids.shape), weights.astype(np.float64))
+    want = so.get_weighted_average(We, ids, w)
+    assert rel_err(fast.double().cpu().numpy(), want) < EMB_RTOL
+    assert rel_err(plain.double().cpu().numpy(), want) < EMB_RTOL
+    assert rel_err(fast.double().cpu().numpy(), plain.double().cpu().numpy()) < 2e-6
+    again, _, _, _ = run(weights, t_ids, True)
+    assert torch.equal(fast, again)                        # deterministic
+    # a zero weight somewhere in the vocabulary: the stand-by general kernel does the work, exactly
+    wz = weights.copy()
+    wz[ids[0, 0]] = 0.0
+    fz, stz, _, _ = run(wz, t_ids, True)
+    pz, _, _, _ = run(wz, t_ids, False)
+    assert stz == 0 and torch.equal(fz, pz)
+    wq = so.seq2weight(ids, np.ones(ids.shape), wz.astype(np.float64))
+    assert rel_err(fz.double().cpu().numpy(), so.get_weighted_average(We, ids, wq)) < EMB_RTOL
+    # an id outside [-V, V)
+    bad = t_ids.clone()
+    bad[17, 2] = V + 3
+    _, stb, _, _ = run(weights, bad, True)
+    assert stb & nv.STATUS_BAD_INDEX
+    # too small a batch: no scratch requested, plain kernel
+    assert lib.mmb_sif_embed_workspace_bytes(V, d, 10, L) == 0
