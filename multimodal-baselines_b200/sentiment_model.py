@@ -233,7 +233,9 @@ def train_sentiment(args, model, train_data, train_latents, valid_data, valid_la
                     loss.backward()
                     optimizer.step()
                     epoch_loss += loss.detach()
-        train_losses.append(float(epoch_loss) / max(n_batches, 1))
+        # graph-captured epochs: keep the epoch's sum on the device (a clone: the next replay overwrites the
+        # graph's static output) and read all of them back once at the end -- no per-epoch stall
+        train_losses.append((epoch_loss.clone() if graph_epochs else float(epoch_loss), max(n_batches, 1)))
         if i % valid_niter == 0:
             batches = 0
             valid_loss = torch.zeros((), device=device)
@@ -242,7 +244,8 @@ def train_sentiment(args, model, train_data, train_latents, valid_data, valid_la
                     valid_loss += _l1(model, valid_latents, valid_labels, j)[0].mean()
                     batches += 1
             avg_valid_loss = float(valid_loss) / max(batches, 1)
-            print("Epoch {}: {} (avg val loss {})".format(i, train_losses[-1], avg_valid_loss))
+            print("Epoch {}: {} (avg val loss {})".format(i, float(train_losses[-1][0]) / train_losses[-1][1],
+                                                          avg_valid_loss))
             is_better = len(valid_losses) == 0 or avg_valid_loss < min(valid_losses)
             valid_losses.append(avg_valid_loss)
             if args['early_stopping']:
@@ -272,6 +275,11 @@ def train_sentiment(args, model, train_data, train_latents, valid_data, valid_la
                             print("early stopping...")
                             break
     print("Epoch {}: {}".format(i, float(epoch_loss) / max(n_samples, 1)))
+    if train_losses and any(torch.is_tensor(v) for v, _ in train_losses):
+        sums = torch.stack([v if torch.is_tensor(v) else torch.tensor(v, device=device) for v, _ in train_losses]).cpu()
+        train_losses = [float(v) / n for v, (_, n) in zip(sums, train_losses)]
+    else:
+        train_losses = [float(v) / n for v, n in train_losses]
     return train_losses, valid_losses
 
 

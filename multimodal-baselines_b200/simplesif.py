@@ -430,6 +430,30 @@ class GraphedStep(object):
         check_status_sink(self.status, list(self.gen_model.embed2out.keys()))
 
 
+class _EpochLosses(list):
+    """Per-epoch loss values that may still live on the device: the graph-captured loops append the epoch's
+    device scalar (a clone: replays overwrite the graph's static output) and nothing waits for it; ``floats()``
+    reads everything back with ONE synchronisation.  The reference reads the value every step
+    (simplesif.py:139 ``float(avg_log_prob)``), which stalls the stream each time."""
+
+    def floats(self):
+        if not self:
+            return []
+        if any(torch.is_tensor(x) for x in self):
+            vals = torch.stack([x if torch.is_tensor(x) else torch.tensor(float(x), device=self._dev()) for x in self])
+            return [float(v) for v in vals.cpu()]
+        return [float(x) for x in self]
+
+    def _dev(self):
+        for x in self:
+            if torch.is_tensor(x):
+                return x.device
+        return 'cpu'
+
+    def last(self):
+        return float(self[-1])
+
+
 def _epoch_index_batches(dataloader, device):
     """The index batches the DataLoader would produce this epoch, drawing from the same RNG in
     the same order (num_workers = 0: one base-seed draw when the iterator is built, then the
@@ -496,7 +520,7 @@ def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epoc
 
     valid_niter = 10
     start_time = time.time()
-    losses = []
+    losses = _EpochLosses()
     all_valid_losses = []
     for i in range(n_epochs):
         epoch_loss = torch.zeros((), device=device)
@@ -505,13 +529,15 @@ def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epoc
             flat, sizes = _epoch_indices(dataloader, device)
             iters = len(sizes)
             if iters:
-                epoch_loss = stepper.run_epoch(flat, sizes)
-            stepper.check()
+                epoch_loss = stepper.run_epoch(flat, sizes).clone()
+            if i % valid_niter == 0 or i == n_epochs - 1:
+                stepper.check()      # one status read per 10 epochs (and at the end), not one per epoch
         elif graphed:
             for j in _epoch_index_batches(dataloader, device):
                 iters += 1
                 epoch_loss += stepper(j)
-            stepper.check()
+            if i % valid_niter == 0 or i == n_epochs - 1:
+                stepper.check()
         else:
             for x in dataloader:
                 j, batch_data, batch_masks = _batch_dicts(args, _with_moments(args, x, moments),
@@ -527,10 +553,10 @@ def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epoc
                 avg_log_prob.backward()
                 optimizer.step()
                 epoch_loss += avg_log_prob.detach()
-        losses.append(float(epoch_loss))
+        losses.append(epoch_loss if graphed else float(epoch_loss))
         if i % valid_niter == 0:
             if verbose:
-                print("epoch {}: {} ({}s)".format(i, losses[-1] / max(iters, 1), time.time() - start_time))
+                print("epoch {}: {} ({}s)".format(i, losses.last() / max(iters, 1), time.time() - start_time))
             if validation_data is not None and i % (valid_niter * 8) == 0:
                 valid_embedding, valid_dataloader = validation_data
                 _, valid_losses = optimize_latents(args, False, gen_model, valid_embedding, valid_dataloader,
@@ -546,7 +572,7 @@ def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epoc
         all_valid_losses.append(valid_losses[0][-1])
 
     embeddings.requires_grad = False
-    return embeddings, (losses, all_valid_losses)
+    return embeddings, (losses.floats(), all_valid_losses)
 
 
 def make_word_log_prob_fn(args, weights, word_embeddings, a=1e-3):
@@ -607,7 +633,7 @@ def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, 
     stepper = GraphedStep(args, gen_model, train_embed, dataloader.dataset, optimizer, word_prob_fn, device,
                           extra_loss=mixed_loss, extra_modules=[senti_model]) if graphed else None
     moments = None if graphed else _dataset_moments(args, dataloader.dataset)
-    train_losses, all_valid_losses = [], []
+    train_losses, all_valid_losses = _EpochLosses(), []
     start_time = time.time()
     n_epochs = n_epochs if n_epochs is not None else args['n_epochs']
     for i in range(n_epochs):
@@ -617,13 +643,15 @@ def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, 
             flat, sizes = _epoch_indices(dataloader, device)
             iters = len(sizes)
             if iters:
-                epoch_loss = stepper.run_epoch(flat, sizes)
-            stepper.check()
+                epoch_loss = stepper.run_epoch(flat, sizes).clone()
+            if i % 10 == 0 or i == n_epochs - 1:
+                stepper.check()
         elif graphed:
             for j in _epoch_index_batches(dataloader, device):
                 iters += 1
                 epoch_loss += stepper(j)
-            stepper.check()
+            if i % 10 == 0 or i == n_epochs - 1:
+                stepper.check()
         else:
             for x in dataloader:
                 j, batch_data, batch_masks = _batch_dicts(args, _with_moments(args, x, moments),
@@ -637,10 +665,10 @@ def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, 
                 loss.backward()
                 optimizer.step()
                 epoch_loss += loss.detach()
-        train_losses.append(float(epoch_loss))
+        train_losses.append(epoch_loss if graphed else float(epoch_loss))
         if i % 10 == 0:
             if verbose:
-                print("epoch {}: {} ({}s)".format(i, train_losses[-1] / max(iters, 1), time.time() - start_time))
+                print("epoch {}: {} ({}s)".format(i, train_losses.last() / max(iters, 1), time.time() - start_time))
             if validation_data is not None and i % 80 == 0:
                 valid_embedding, valid_dataloader = validation_data
                 _, (valid_losses, _) = optimize_latents(args, False, gen_model, valid_embedding, valid_dataloader,
@@ -649,7 +677,7 @@ def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, 
                     print("Validation loss:", valid_losses[-1])
                 all_valid_losses.append(valid_losses[-1])
     train_embed.requires_grad = False
-    return train_embed, (train_losses, all_valid_losses)
+    return train_embed, (train_losses.floats(), all_valid_losses)
 
 
 def read_config(config_file):
