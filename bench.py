@@ -280,16 +280,19 @@ def load_ncu_record(kernel, ids_kind):
 
 def time_embed_only(lib, nv, table, vocab_w, ids, reps=5, warm=3):
     """CUDA-event time of the embed kernel alone on `ids` (current stream)."""
+    import sif_dist as mdist
     n, L = ids.shape
     V, d = table.shape
     emb = torch.empty((n, d), dtype=torch.float32, device=ids.device)
     st = torch.zeros(1, dtype=torch.int32, device=ids.device)
+    ws_bytes = lib.mmb_sif_embed_workspace_bytes(V, d, n, L)         # the same entry point the timed step uses
+    ws = mdist._embed_scratch(ws_bytes, ids.device) if ws_bytes else None
     ms = []
     for it in range(warm + reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        nv.check(lib.mmb_sif_embed(nv.ptr(table), V, d, nv.ptr(vocab_w), nv.ptr(ids), n, L, nv.ptr(emb), nv.ptr(st),
-                                   nv.stream_ptr()))
+        nv.check(lib.mmb_sif_embed_ws(nv.ptr(table), V, d, nv.ptr(vocab_w), nv.ptr(ids), n, L, nv.ptr(emb), nv.ptr(st),
+                                      nv.ptr(ws), ws_bytes, nv.stream_ptr()))
         e1.record()
         e1.synchronize()
         if it >= warm:

@@ -72,6 +72,9 @@ MMB_API unsigned long long mmb_launch_count(void);
 MMB_API const char* mmb_last_kernel(int tag);
 /* Pinned host memory for the *_host entry points and for e2e benchmarks. */
 MMB_API int mmb_host_alloc(void** ptr, size_t bytes);
+/* Write-combined pinned memory: for buffers the host only WRITES and the device reads (the ids of the
+ * *_host entry points); not snooped by the CPU caches on its way over PCIe, slow for host reads. */
+MMB_API int mmb_host_alloc_wc(void** ptr, size_t bytes);
 MMB_API int mmb_host_free(void* ptr);
 
 /* ---------------------------------------------------------------- SIF (A1-A5) ----- */
@@ -238,6 +241,14 @@ MMB_API int mmb_heads_backward(const float* z, int B, int d, int n_heads, const 
                        const int* D, const float* const* gout, float* dz, float* const* dW,
                        float* const* db, void* ws, size_t ws_bytes, mmb_stream_t stream);
 
+/* get_log_prob_matrix's combination -- losses.py:267-272: out[b] = other_w * sum_m lp[m][b] + word_w * wlp[b]
+ * (lp is (M, B) row-major) and its backward, one launch each instead of torch's sum / mul / mul / add chain.
+ * When other_w_dev / word_w_dev are non-NULL the weights are read from those device scalars instead.   */
+MMB_API int mmb_combine_lp(const float* lp, const float* wlp, int M, int B, float other_w, float word_w,
+                           const float* other_w_dev, const float* word_w_dev, float* out, mmb_stream_t stream);
+MMB_API int mmb_combine_lp_backward(const float* g, int M, int B, float other_w, float word_w,
+                                    const float* other_w_dev, const float* word_w_dev, float* g_lp, float* g_wlp,
+                                    mmb_stream_t stream);
 /* Launch-count helpers of the step (B = 64: every torch element-wise op is a launch).
  * mmb_scale_multi: out[i] (B, D[i]) = in[i] * row[i][b] * elem[i][b][f] for n <= 16 tensors in one
  * launch (row / elem tables or entries may be NULL = 1): the chain rule through the per-modality

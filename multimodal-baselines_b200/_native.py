@@ -35,6 +35,7 @@ SIGNATURES = {
     'mmb_launch_count': (C.c_ulonglong, []),
     'mmb_last_kernel': (C.c_char_p, [_i]),
     'mmb_host_alloc': (_i, [C.POINTER(_p), _sz]),
+    'mmb_host_alloc_wc': (_i, [C.POINTER(_p), _sz]),
     'mmb_host_free': (_i, [_p]),
     'mmb_seq2weight': (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p]),
     'mmb_weighted_average': (_i, [_p, _i64, _i, _p, _p, _i64, _i64, _p, _p, _p]),
@@ -71,6 +72,8 @@ SIGNATURES = {
     'mmb_heads_backward_workspace_bytes': (_sz, [_i, _i, _i, _p]),
     'mmb_heads_backward': (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     'mmb_scale_multi': (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
+    'mmb_combine_lp': (_i, [_p, _p, _i, _i, _f, _f, _p, _p, _p, _p]),
+    'mmb_combine_lp_backward': (_i, [_p, _i, _i, _f, _f, _p, _p, _p, _p, _p]),
     'mmb_gather_multi': (_i, [_i, _i, _p, _p, _p, _p, _p]),
     'mmb_gauss_ll': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'mmb_closed_form_stats': (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -164,12 +167,12 @@ def raise_on_status(status_tensor, V=None):
 class PinnedArray:
     """A NumPy array backed by cudaHostAlloc memory (full PCIe rate for the *_host calls)."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, write_combined=False):
         self.dtype = np.dtype(dtype)
         self.shape = tuple(int(s) for s in np.atleast_1d(shape))
         nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
         self._ptr = C.c_void_p()
-        check(lib.mmb_host_alloc(C.byref(self._ptr), nbytes))
+        check((lib.mmb_host_alloc_wc if write_combined else lib.mmb_host_alloc)(C.byref(self._ptr), nbytes))
         buf = (C.c_char * max(nbytes, 1)).from_address(self._ptr.value)
         self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
 

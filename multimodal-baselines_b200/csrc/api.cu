@@ -104,6 +104,12 @@ extern "C" int mmb_host_alloc(void** ptr, size_t bytes) {
   return MMB_OK;
 }
 
+extern "C" int mmb_host_alloc_wc(void** ptr, size_t bytes) {
+  MMB_REQUIRE(ptr, "null pointer");
+  MMB_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocWriteCombined));
+  return MMB_OK;
+}
+
 extern "C" int mmb_host_free(void* ptr) {
   if (ptr) MMB_CUDA(cudaFreeHost(ptr));
   return MMB_OK;

@@ -127,6 +127,35 @@ __global__ void __launch_bounds__(128) scale_multi_kernel(const __grid_constant_
   for (int f = threadIdx.x; f < D; f += blockDim.x) out[f] = in[f] * r * (el ? __ldg(el + f) : 1.f);
 }
 
+// The combination step of get_log_prob_matrix (reference losses.py:267-272) in one launch each way:
+//   out[b]      = other_w * sum_m lp[m][b] + word_w * wlp[b]
+//   g_lp[m][b]  = other_w * g[b],   g_wlp[b] = word_w * g[b]
+// (torch: sum, two multiplies, an add and their four backward nodes.)  other_w / word_w may come from
+// device scalars (ow_dev / ww_dev non-NULL): a captured graph then serves every grid point's weights.
+__global__ void __launch_bounds__(256)
+    combine_lp_kernel(const float* __restrict__ lp, const float* __restrict__ wlp, int M, int B, float ow, float ww,
+                      const float* __restrict__ ow_dev, const float* __restrict__ ww_dev, float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (ow_dev) ow = __ldg(ow_dev);
+  if (ww_dev) ww = __ldg(ww_dev);
+  float s = 0.f;
+  for (int m = 0; m < M; ++m) s += lp[(size_t)m * B + b];      // modality order, as torch's sum(0)
+  out[b] = __fadd_rn(__fmul_rn(s, ow), __fmul_rn(ww, wlp[b]));   // torch's two products and their sum, unfused
+}
+__global__ void __launch_bounds__(256)
+    combine_lp_bwd_kernel(const float* __restrict__ g, int M, int B, float ow, float ww,
+                          const float* __restrict__ ow_dev, const float* __restrict__ ww_dev,
+                          float* __restrict__ g_lp, float* __restrict__ g_wlp) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (ow_dev) ow = __ldg(ow_dev);
+  if (ww_dev) ww = __ldg(ww_dev);
+  const float gb = g[b];
+  for (int m = 0; m < M; ++m) g_lp[(size_t)m * B + b] = ow * gb;
+  g_wlp[b] = ww * gb;
+}
+
 struct GatherArgs {
   const float* src[kMaxMulti];    // (N_i, W[i]) row-major
   float* dst[kMaxMulti];          // (B, W[i])
@@ -762,6 +791,25 @@ extern "C" int mmb_scale_multi(int n, int B, const int* D, const float* const* i
   a.n = n;
   scale_multi_kernel<<<dim3(B, n), 128, 0, as_stream(stream)>>>(a);
   MMB_LAUNCH_CHECK("scale_multi");
+  return MMB_OK;
+}
+
+extern "C" int mmb_combine_lp(const float* lp, const float* wlp, int M, int B, float other_w, float word_w,
+                              const float* other_w_dev, const float* word_w_dev, float* out, mmb_stream_t stream) {
+  MMB_REQUIRE(lp && wlp && out && M > 0 && B > 0, "bad argument");
+  combine_lp_kernel<<<(B + 255) / 256, 256, 0, as_stream(stream)>>>(lp, wlp, M, B, other_w, word_w, other_w_dev,
+                                                                     word_w_dev, out);
+  MMB_LAUNCH_CHECK("combine_lp");
+  return MMB_OK;
+}
+
+extern "C" int mmb_combine_lp_backward(const float* g, int M, int B, float other_w, float word_w,
+                                       const float* other_w_dev, const float* word_w_dev, float* g_lp, float* g_wlp,
+                                       mmb_stream_t stream) {
+  MMB_REQUIRE(g && g_lp && g_wlp && M > 0 && B > 0, "bad argument");
+  combine_lp_bwd_kernel<<<(B + 255) / 256, 256, 0, as_stream(stream)>>>(g, M, B, other_w, word_w, other_w_dev,
+                                                                         word_w_dev, g_lp, g_wlp);
+  MMB_LAUNCH_CHECK("combine_lp_bwd");
   return MMB_OK;
 }
 

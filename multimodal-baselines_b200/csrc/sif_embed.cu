@@ -557,11 +557,14 @@ __global__ void __launch_bounds__(1024)
 // CTA-per-utterance variant (few, long utterances -- the POM shape: 203 x 1357): the 8
 // warps take 32-token chunks round-robin and are summed through shared memory in warp
 // order, so the result is still deterministic.
+// With `offsets` (ragged ids, see sif_embed_ragged_kernel) utterance i is ids[offsets[i] .. offsets[i+1]) followed
+// by L - length copies of pad_id, whose closed-form term warp 0 adds.
 template <int NCH, bool EXPLICIT_W>
 __global__ void __launch_bounds__(kEmbedWarps * 32)
     sif_embed_cta_kernel(const float4* __restrict__ table4, int V, int d4,
                          const float* __restrict__ wsrc, const int64_t* __restrict__ ids, int64_t N,
-                         int64_t L, float4* __restrict__ emb4, int* __restrict__ status) {
+                         int64_t L, float4* __restrict__ emb4, int* __restrict__ status,
+                         const int64_t* __restrict__ offsets = nullptr, int64_t pad_id = 0) {
   __shared__ float4 part[kEmbedWarps][NCH * 32];
   __shared__ int part_cnt[kEmbedWarps];
   const int lane = threadIdx.x & 31;
@@ -574,11 +577,26 @@ __global__ void __launch_bounds__(kEmbedWarps * 32)
     RowAcc<NCH> acc;
     acc.clear();
     int cnt = 0;
-    const int64_t* row_ids = ids + i * L;
+    const int64_t o0 = offsets ? __ldg(offsets + i) : i * L;
+    const int64_t len = offsets ? __ldg(offsets + i + 1) - o0 : L;
+    const int64_t* row_ids = ids + o0;
     const float* row_w = EXPLICIT_W ? wsrc + i * L : nullptr;
-    for (int64_t base = 32 * (int64_t)warp; base < L; base += 32 * kEmbedWarps)
+    for (int64_t base = 32 * (int64_t)warp; base < len; base += 32 * kEmbedWarps)
       cnt += accumulate_chunk<NCH, EXPLICIT_W, 2, true>(acc, lane_base, V, row_bytes, tail, wsrc, row_ids, row_w,
-                                                        base, L, lane, bad);
+                                                        base, len, lane, bad);
+    if (!EXPLICIT_W && offsets && warp == 0) {
+      const int64_t n_pad = L - len;
+      const int64_t pad_row = pad_id < 0 ? pad_id + V : pad_id;
+      if (n_pad > 0 && pad_row >= 0 && pad_row < V) {
+        const float pad_w = pad_id >= 0 ? __ldg(wsrc + pad_id) : 0.f;
+        float4 v[NCH];
+        load_row<NCH>(v, lane_base, (size_t)pad_row * row_bytes, tail);
+        fma_row<NCH>(acc, v, (float)n_pad * pad_w, tail);
+        if (pad_w != 0.f) cnt += (int)n_pad;
+      } else if (n_pad != 0) {
+        bad = true;
+      }
+    }
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -744,12 +762,20 @@ extern "C" int mmb_sif_embed_ragged(const float* table, int64_t V, int d, const 
   MMB_REQUIRE(((uintptr_t)table % 16 == 0) && ((uintptr_t)emb % 16 == 0), "table/emb must be 16-byte aligned");
   const int sms = sm_count();
   const int64_t blocks = ceil_div(N, kEmbedWarps);
-  const int grid = (int)(blocks < (int64_t)sms * 8 ? blocks : (int64_t)sms * 8);
   const int d4 = d / 4;
   cudaStream_t st = as_stream(stream);
-#define RAGGED_LAUNCH(NCH)                                                                          \
-  sif_embed_ragged_kernel<NCH, 2, 4><<<grid, kEmbedWarps * 32, 0, st>>>(                            \
-      (const float4*)table, (int)V, d4, vocab_w, tokens, offsets, N, L_pad, pad_id, (float4*)emb, status)
+  // few, long utterances (the POM shape): a CTA per utterance, its 8 warps take the 32-token chunks round-robin and
+  // are summed in warp order -- parallelism for a handful of rows, and 8 short partial sums instead of one long one
+  const bool few_long = (L_pad >= 256) && (N < (int64_t)sms * 16);
+  const int grid = few_long ? (int)(N < (int64_t)sms * 8 ? N : (int64_t)sms * 8)
+                            : (int)(blocks < (int64_t)sms * 8 ? blocks : (int64_t)sms * 8);
+#define RAGGED_LAUNCH(NCH)                                                                                   \
+  if (few_long)                                                                                              \
+    sif_embed_cta_kernel<NCH, false><<<grid, kEmbedWarps * 32, 0, st>>>(                                     \
+        (const float4*)table, (int)V, d4, vocab_w, tokens, N, L_pad, (float4*)emb, status, offsets, pad_id); \
+  else                                                                                                       \
+    sif_embed_ragged_kernel<NCH, 2, 4><<<grid, kEmbedWarps * 32, 0, st>>>(                                   \
+        (const float4*)table, (int)V, d4, vocab_w, tokens, offsets, N, L_pad, pad_id, (float4*)emb, status)
   switch ((d4 + 31) / 32) {
     case 1: RAGGED_LAUNCH(1); break;
     case 2: RAGGED_LAUNCH(2); break;
@@ -758,7 +784,7 @@ extern "C" int mmb_sif_embed_ragged(const float* table, int64_t V, int d, const 
   }
 #undef RAGGED_LAUNCH
   MMB_LAUNCH_CHECK("sif_embed_ragged");
-  note_kernel(0, "sif_embed_ragged_kernel");
+  note_kernel(0, few_long ? "sif_embed_cta_kernel (ragged)" : "sif_embed_ragged_kernel");
   return MMB_OK;
 }
 

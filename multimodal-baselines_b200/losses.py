@@ -254,9 +254,10 @@ def get_log_prob_matrix(args, latents, out, data, masks, word_log_prob_fn,
     if verbose:
         print({m: float(lp[i].min()) for i, m in enumerate(names)}, float(word_log_prob.min()))
 
-    total = lp.sum(0)
+    # the combination of lines 267-272 as one launch each way (mmb_combine_lp) instead of sum / mul / mul / add
     if 'word_loss_weight' in args:
         word_weight = args['word_loss_weight']
         other_weight = (1. - word_weight) / len(names)
-        return total * other_weight + word_weight * word_log_prob
-    return total + word_log_prob
+    else:
+        word_weight = other_weight = 1.
+    return mmb_ops.CombineLPFunction.apply(lp, word_log_prob, other_weight, word_weight)

@@ -230,6 +230,31 @@ class GaussLLStatsFunction(torch.autograd.Function):
     backward = staticmethod(GaussLLFunction.backward)
 
 
+class CombineLPFunction(torch.autograd.Function):
+    """``other_w * lp.sum(0) + word_w * wlp`` (reference losses.py:267-272) with its backward, one launch each
+    way (``mmb_combine_lp``).  lp (M, B), wlp (B,) -> (B,)."""
+
+    @staticmethod
+    def forward(ctx, lp, wlp, other_w, word_w):
+        lp, wlp = _f32(lp), _f32(wlp)
+        M, B = lp.shape
+        out = torch.empty(B, dtype=torch.float32, device=lp.device)
+        nv.check(lib.mmb_combine_lp(nv.ptr(lp), nv.ptr(wlp), M, B, float(other_w), float(word_w), None, None,
+                                    nv.ptr(out), nv.stream_ptr()))
+        ctx.w = (float(other_w), float(word_w), M, B)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ow, ww, M, B = ctx.w
+        g = _f32(g)
+        g_lp = torch.empty((M, B), dtype=torch.float32, device=g.device)
+        g_wlp = torch.empty(B, dtype=torch.float32, device=g.device)
+        nv.check(lib.mmb_combine_lp_backward(nv.ptr(g), M, B, ow, ww, None, None, nv.ptr(g_lp), nv.ptr(g_wlp),
+                                             nv.stream_ptr()))
+        return g_lp, g_wlp, None, None
+
+
 class WordLLFunction(torch.autograd.Function):
     """Angular word log-probability (reference losses.py:68-95) with its gradient w.r.t. the
     latents; the word table, token vectors, weights and mask are constants of the step."""

@@ -1,5 +1,6 @@
 """Small driver for ncu: one launch of each SIF kernel at a 2M-utterance slice of the bench
-workload (same distributions as bench.py)."""
+workload (same distributions as bench.py; sif_embedding_device takes the pre-scaled-table embed path for
+batches of this size, exactly as bench.py's timed step does)."""
 import os
 import sys
 
