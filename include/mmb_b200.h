@@ -70,6 +70,10 @@ MMB_API int mmb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * mmb_weighted_average).  bench.py derives `gpu_launches` and `roofline.kernel` from these. */
 MMB_API unsigned long long mmb_launch_count(void);
 MMB_API const char* mmb_last_kernel(int tag);
+/* Run-time switches for experiments and tests (the defaults are what the benchmarks use):
+ *   "embed_prescale"  1 (default) / 0: fold the vocabulary weights into a scratch table for large batches
+ *   "embed_hot"       0 / 1: the tensor-core hot-row embed path for very large batches (d = 300)      */
+MMB_API int mmb_set_option(const char* name, int value);
 /* Pinned host memory for the *_host entry points and for e2e benchmarks. */
 MMB_API int mmb_host_alloc(void** ptr, size_t bytes);
 /* Write-combined pinned memory: for buffers the host only WRITES and the device reads (the ids of the

@@ -32,6 +32,7 @@ SIGNATURES = {
     'mmb_version': (_i, []),
     'mmb_last_error': (C.c_char_p, []),
     'mmb_device_info': (_i, [C.POINTER(_i)] * 3),
+    'mmb_set_option': (_i, [C.c_char_p, _i]),
     'mmb_launch_count': (C.c_ulonglong, []),
     'mmb_last_kernel': (C.c_char_p, [_i]),
     'mmb_host_alloc': (_i, [C.POINTER(_p), _sz]),

@@ -35,6 +35,19 @@ void note_kernel(int tag, const char* name) {
   strncpy(g_last_kernel[tag], name, sizeof(g_last_kernel[tag]) - 1);
 }
 
+// Run-time switches (mmb_set_option); -1 = unset -> the environment variable / built-in default decides.
+static int g_opt_embed_hot = -1, g_opt_embed_prescale = -1;
+int option_embed_hot() {
+  if (g_opt_embed_hot >= 0) return g_opt_embed_hot;
+  static const int env = getenv("MMB_EMBED_HOT") ? atoi(getenv("MMB_EMBED_HOT")) : 0;
+  return env;
+}
+int option_embed_prescale() {
+  if (g_opt_embed_prescale >= 0) return g_opt_embed_prescale;
+  static const int env = getenv("MMB_EMBED_PRESCALE") ? atoi(getenv("MMB_EMBED_PRESCALE")) : 1;
+  return env;
+}
+
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 148;
   int dev = 0;
@@ -86,6 +99,17 @@ extern "C" const char* mmb_last_error(void) { return g_err; }
 extern "C" unsigned long long mmb_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 extern "C" const char* mmb_last_kernel(int tag) { return (tag >= 0 && tag < 8) ? g_last_kernel[tag] : ""; }
+
+extern "C" int mmb_set_option(const char* name, int value) {
+  MMB_REQUIRE(name, "null pointer");
+  if (!strcmp(name, "embed_hot")) g_opt_embed_hot = value;
+  else if (!strcmp(name, "embed_prescale")) g_opt_embed_prescale = value;
+  else {
+    set_error("mmb_set_option: unknown option '%s'", name);
+    return MMB_E_INVALID;
+  }
+  return MMB_OK;
+}
 
 extern "C" int mmb_device_info(int* sm, int* cc_major, int* cc_minor) {
   int dev = 0;

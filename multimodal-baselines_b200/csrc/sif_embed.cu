@@ -816,14 +816,22 @@ extern "C" int mmb_ids_compact(const int64_t* ids, int64_t N, int64_t L, const i
   return MMB_OK;
 }
 
+namespace mmb {   // sif_embed_hot.cu
+size_t sif_embed_hot_extra_bytes(int64_t V);
+bool sif_embed_hot_eligible(int64_t V, int d, int64_t N, int64_t L);
+int sif_embed_hot(const float* tp, const int* flags, int64_t V, const int64_t* x, int64_t N, int64_t L, float* emb,
+                  int* status, void* ws_hot, cudaStream_t st);
+}  // namespace mmb
+
 extern "C" size_t mmb_sif_embed_workspace_bytes(int64_t V, int d, int64_t N, int64_t L) {
   // pre-scaled table + flag word; 0 = the batch is too small for the pre-scale pass to pay (or out of range)
-  static const bool off = getenv("MMB_EMBED_PRESCALE") && atoi(getenv("MMB_EMBED_PRESCALE")) == 0;
+  const bool off = option_embed_prescale() == 0;
   if (off || d <= 0 || d % 4 != 0 || d > 512 || V <= 0 || V >= ((int64_t)1 << kRowBits)) return 0;
   if ((uint64_t)V * (uint64_t)d * 4u >= ((uint64_t)1 << 32)) return 0;
   if (L >= 256 && N < (int64_t)sm_count() * 16) return 0;     // few long rows: the CTA-per-utterance kernel
   if (N * L < 8 * V) return 0;
-  return (size_t)V * d * sizeof(float) + 256;
+  // (+ the sample histogram and hot-id list of the tensor-core hot-row path; unused below its threshold)
+  return (size_t)V * d * sizeof(float) + 256 + sif_embed_hot_extra_bytes(V);
 }
 
 namespace mmb {
@@ -847,6 +855,17 @@ int sif_embed_prescaled(const float* table, int64_t V, int d, const float* vocab
   const int sms = sm_count();
   const int64_t blocks = ceil_div(N, kEmbedWarps);
   const int grid = (int)(blocks < (int64_t)sms * 8 ? blocks : (int64_t)sms * 8);
+  if (sif_embed_hot_eligible(V, d, N, L)) {
+    // very large batches: the most frequent rows on the tensor cores (sif_embed_hot.cu); the general kernel
+    // still stands by for the zero-weight case
+    void* ws_hot = (void*)((char*)ws + 256 + (size_t)V * d * sizeof(float));
+    int rc = sif_embed_hot((const float*)tp4, flags, V, x, N, L, emb, status, ws_hot, st);
+    if (rc) return rc;
+    sif_embed_warp_prefetch_kernel<3, 2, 4><<<grid, kEmbedWarps * 32, 0, st>>>(
+        (const float4*)table, (int)V, d4, vocab_w, x, N, L, (float4*)emb, status, flags);
+    MMB_LAUNCH_CHECK("sif_embed_general_standby");
+    return MMB_OK;
+  }
   static const int variant = getenv("MMB_EMBED_PS_VARIANT") ? atoi(getenv("MMB_EMBED_PS_VARIANT")) : 0;
 #define PS_KERNEL(NCH, U, B)                                                                                   \
   sif_embed_prescaled_kernel<NCH, U, B><<<grid, kEmbedWarps * 32, 0, st>>>(tp4, (int)V, d4, flags, x, N, L,    \

@@ -1,0 +1,68 @@
+"""GPU check of the tensor-core hot-row embed path (csrc/sif_embed_hot.cu) against the pre-scaled gather kernel and
+the NumPy oracle, plus a timing of both at a slice of the bench workload.   python tools/embed_hot_check.py [N]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'multimodal-baselines_b200'))
+import numpy as np
+import torch
+import bench
+import _native as nv
+from _native import lib
+from oracle import sif_oracle as so
+
+
+def run(table, vw, ids, hot):
+    nv.check(lib.mmb_set_option(b'embed_hot', int(hot)))
+    n, L = ids.shape
+    V, d = table.shape
+    emb = torch.empty((n, d), dtype=torch.float32, device=ids.device)
+    st = torch.zeros(1, dtype=torch.int32, device=ids.device)
+    nbytes = lib.mmb_sif_embed_workspace_bytes(V, d, n, L)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=ids.device)
+    ms = []
+    for it in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        nv.check(lib.mmb_sif_embed_ws(nv.ptr(table), V, d, nv.ptr(vw), nv.ptr(ids), n, L, nv.ptr(emb), nv.ptr(st),
+                                      nv.ptr(ws), nbytes, nv.stream_ptr()))
+        e1.record()
+        e1.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    return emb, int(st.item()), float(np.mean(ms[2:])), (lib.mmb_last_kernel(0) or b'').decode()
+
+
+def rel(got, want):
+    scale = want.abs().amax(dim=-1, keepdim=True).clamp_min(1e-30)
+    return float(((got - want).abs() / scale).max())
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
+    dev = torch.device('cuda')
+    ok = True
+    for V, nn, L in ((3000, 40_000, 20), (bench.VOCAB, n, bench.L_TOK)):
+        table, vw, p = bench.make_table_and_weights(dev, V=V)
+        ids = bench.make_ids(dev, nn, L, p, seed=1000)
+        ids[3, 1] = -5                     # a negative id: wraps, weight 0
+        ref, st0, ms0, k0 = run(table, vw, ids, 0)
+        hot, st1, ms1, k1 = run(table, vw, ids, 1)
+        again, _, _, _ = run(table, vw, ids, 1)
+        err = rel(hot.double(), ref.double())
+        rows = torch.cat([torch.arange(0, 300), torch.arange(nn - 300, nn)]).to(dev)
+        ids_np = ids[rows].cpu().numpy()
+        w_np = so.seq2weight(ids_np, np.ones(ids_np.shape), vw.double().cpu().numpy())
+        want = torch.as_tensor(so.get_weighted_average(table.cpu().numpy(), ids_np, w_np))
+        e_or0, e_or1 = rel(ref[rows].double().cpu(), want), rel(hot[rows].double().cpu(), want)
+        good = err < 5e-6 and e_or1 < 1e-5 and st0 == 0 and st1 == 0 and torch.equal(hot, again) and 'hot' in k1
+        ok = ok and good
+        print('V=%d N=%d L=%d: %s %.3f ms | %s %.3f ms | hot vs gather %.2e, vs oracle: gather %.2e hot %.2e, '
+              'deterministic %s -> %s' % (V, nn, L, k0, ms0, k1, ms1, err, e_or0, e_or1, torch.equal(hot, again),
+                                          'ok' if good else 'FAIL'), flush=True)
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == '__main__':
+    main()
