@@ -694,6 +694,25 @@ def main():
         del ids
         torch.cuda.empty_cache()
         secondary = {'mmb2_step': mmb_secondary()}
+    if world > 1 and not args.no_secondary:
+        # SURVEY.md 8e "MMB training" on this process group: the data-parallel latent optimisation must reproduce
+        # the reference loop's goldens with the utterances sharded over the ranks (head gradients summed over NVLink
+        # peer memory, global-batch mean, synchronised BatchNorm), then one B = 512 step is timed
+        try:
+            sys.path.insert(0, os.path.join(ROOT, 'tools'))
+            sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+            import dp_check
+            ok_dp, lines = dp_check.check_goldens(rank, world, dev)
+            step = dp_check.time_step(rank, world, dev)
+            fl = torch.tensor([0 if ok_dp else 1], device=dev)
+            dist.all_reduce(fl)
+            secondary = {'mmb2_step_data_parallel': dict(step, goldens_reproduced=int(fl.item()) == 0,
+                                                         rank0_checks=lines)}
+            if verify is not None:
+                verify['dp_mmb_goldens'] = int(fl.item()) == 0
+                verify['ok'] = verify['ok'] and verify['dp_mmb_goldens']
+        except Exception as e:
+            secondary = {'mmb2_step_data_parallel': {'error': '%s: %s' % (type(e).__name__, e)}}
     sampler.stop()
 
     if rank == 0:

@@ -36,7 +36,12 @@ void note_kernel(int tag, const char* name) {
 }
 
 // Run-time switches (mmb_set_option); -1 = unset -> the environment variable / built-in default decides.
-static int g_opt_embed_hot = -1, g_opt_embed_prescale = -1;
+static int g_opt_embed_hot = -1, g_opt_embed_prescale = -1, g_opt_embed_warm = -1;
+int option_embed_warm() {
+  if (g_opt_embed_warm >= 0) return g_opt_embed_warm;
+  static const int env = getenv("MMB_EMBED_WARM") ? atoi(getenv("MMB_EMBED_WARM")) : 0;
+  return env < 0 ? 0 : (env > 512 ? 512 : env);
+}
 int option_embed_hot() {
   if (g_opt_embed_hot >= 0) return g_opt_embed_hot;
   static const int env = getenv("MMB_EMBED_HOT") ? atoi(getenv("MMB_EMBED_HOT")) : 0;
@@ -104,6 +109,7 @@ extern "C" int mmb_set_option(const char* name, int value) {
   MMB_REQUIRE(name, "null pointer");
   if (!strcmp(name, "embed_hot")) g_opt_embed_hot = value;
   else if (!strcmp(name, "embed_prescale")) g_opt_embed_prescale = value;
+  else if (!strcmp(name, "embed_warm")) g_opt_embed_warm = value < 0 ? 0 : (value > 512 ? 512 : value);
   else {
     set_error("mmb_set_option: unknown option '%s'", name);
     return MMB_E_INVALID;

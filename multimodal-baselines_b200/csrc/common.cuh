@@ -27,6 +27,7 @@ int sm_count();
 void count_launch(const char* name);
 void note_kernel(int tag, const char* name);
 int option_embed_hot();        // 1: the tensor-core hot-row embed path for very large batches (sif_embed_hot.cu)
+int option_embed_warm();       // K > 0: keep only the K most frequent rows cacheable in L1 (sif_embed_prescaled_warm_kernel)
 int option_embed_prescale();   // 0: never fold the weights into a scratch table (always the general kernel)
 
 #define MMB_LAUNCH_CHECK(name)                                    \

@@ -421,6 +421,114 @@ __global__ void __launch_bounds__(kEmbedWarps * 32, MINB)
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, MMB_STATUS_BAD_INDEX);
 }
 
+// The same kernel with an L1 allocation policy per row.  After the pre-scale the kernel is bound by the L2 -> SM
+// fabric (ncu r02b: 25 KB per utterance at 11.2 TB/s = 91 % of the LTS cap): every row that misses L1 crosses it,
+// and under LRU the cold rows (each read once, 10 lines) keep evicting the few hundred warm rows that would be
+// read again.  A sample histogram of the ids (sif_embed_hot.cu: hot_hist / hot_select) names the K most frequent
+// rows; each CTA keeps a 64 Kbit Bloom filter of them in shared memory, and rows that are NOT in it are loaded with
+// ld.global.nc.L1::no_allocate (SASS LDG.E.NA): the L1 is left to the rows that will hit again.  Results are
+// bit-identical to sif_embed_prescaled_kernel (only the cache policy differs).
+constexpr int kBloomWords = 2048;      // 8 KB per CTA
+constexpr int kWarmRowBits = 25;       // row index below 2^25, multiplicity (<= 32) in 6 bits, warm flag in bit 31
+__device__ __forceinline__ unsigned bloom_hash(unsigned row) { return (row * 2654435761u) >> 16; }
+
+template <int NCH>
+__device__ __forceinline__ void load_row_na(float4 (&v)[NCH], const char* __restrict__ lane_base, size_t off,
+                                            typename Live<NCH>::type live) {
+  const float4* p = (const float4*)(lane_base + off);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+    if (chunk_on<NCH>(live, c))
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v[c].x), "=f"(v[c].y), "=f"(v[c].z), "=f"(v[c].w) : "l"(p + 32 * c));
+}
+
+template <int NCH, int UNROLL, int MINB>
+__global__ void __launch_bounds__(kEmbedWarps * 32, MINB)
+    sif_embed_prescaled_warm_kernel(const float4* __restrict__ tp4, int V, int d4, const int* __restrict__ flags,
+                                    const int* __restrict__ warm_ids, int n_warm, const int64_t* __restrict__ ids,
+                                    int64_t N, int64_t L, float4* __restrict__ emb4, int* __restrict__ status) {
+  if (__ldg(flags) & 1) return;        // a zero vocabulary weight: the general kernel behind this one runs
+  __shared__ unsigned bloom[kBloomWords];
+  for (int i = threadIdx.x; i < kBloomWords; i += blockDim.x) bloom[i] = 0u;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_warm; i += blockDim.x) {
+    const int id = __ldg(warm_ids + i);
+    if (id >= 0) {
+      const unsigned h = bloom_hash((unsigned)id);
+      atomicOr(&bloom[h >> 5], 1u << (h & 31u));
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kEmbedWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kEmbedWarps;
+  const char* lane_base = (const char*)(tp4 + lane);
+  const unsigned row_bytes = (unsigned)d4 * 16u;
+  const typename Live<NCH>::type tail = make_live<NCH>(lane, d4);
+  constexpr unsigned kRowMask = (1u << kWarmRowBits) - 1u;
+  bool bad = false;
+  int64_t nid = (warp0 < N && lane < L) ? __ldcs(ids + warp0 * L + lane) : 0;
+  for (int64_t i = warp0; i < N; i += nwarps) {
+    RowAcc<NCH> acc;
+    acc.clear();
+    int cnt = 0;
+    for (int64_t base = 0; base < L; base += 32) {
+      const int64_t id = nid;
+      const bool same = base + 32 < L;
+      const int64_t ni = same ? i : i + nwarps;
+      const int64_t nb = same ? base + 32 : 0;
+      nid = (ni < N && nb + lane < L) ? __ldcs(ids + ni * L + nb + lane) : 0;
+      int row = -1;
+      bool counts = false;
+      unsigned warm = 0u;
+      if (base + lane < L) {
+        const int64_t r = id < 0 ? id + V : id;
+        if (r >= 0 && r < V) {
+          row = (int)r;
+          counts = id >= 0;
+          const unsigned h = bloom_hash((unsigned)row);
+          warm = (bloom[h >> 5] >> (h & 31u)) & 1u;
+        } else {
+          bad = true;
+        }
+      }
+      const unsigned nn = __ballot_sync(0xffffffffu, counts);
+      cnt += __popc(nn);
+      const unsigned grp = __match_any_sync(0xffffffffu, row);
+      const bool head = (row >= 0) && (lane == __ffs(grp) - 1);
+      const unsigned packed = (unsigned)row | ((unsigned)__popc(grp & nn) << kWarmRowBits) | (warm << 31);
+      unsigned heads = __ballot_sync(0xffffffffu, head);
+      while (heads) {
+        int j[UNROLL];
+        int n = 0;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          j[u] = heads ? (__ffs(heads) - 1) : 0;
+          if (heads) { heads &= heads - 1; ++n; }
+        }
+        float mj[UNROLL];
+        float4 v[UNROLL][NCH];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          if (u < n) {
+            const unsigned pj = __shfl_sync(0xffffffffu, packed, j[u]);
+            mj[u] = (float)((pj >> kWarmRowBits) & 63u);
+            const unsigned off = (pj & kRowMask) * row_bytes;
+            if (pj >> 31) load_row<NCH>(v[u], lane_base, off, tail);       // warm: keep it in L1
+            else load_row_na<NCH>(v[u], lane_base, off, tail);             // cold: do not displace the warm rows
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          if (u < n) fma_row<NCH>(acc, v[u], mj[u], tail);
+      }
+    }
+    store_row<NCH>(emb4 + (size_t)i * d4, acc, cnt, lane, d4);
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, MMB_STATUS_BAD_INDEX);
+}
+
 // Ragged (CSR) variant, SURVEY.md 8f N3: utterance i is tokens[offsets[i] .. offsets[i+1]) -- what is left of a
 // right-padded row once its trailing run of the pad id is cut off (utils.py:77-80 pads POM to 1089 / 1357
 // tokens: 73 % of that fixture is padding, 37 % of the bench workload).  The reference still sums the pad
@@ -821,6 +929,8 @@ size_t sif_embed_hot_extra_bytes(int64_t V);
 bool sif_embed_hot_eligible(int64_t V, int d, int64_t N, int64_t L);
 int sif_embed_hot(const float* tp, const int* flags, int64_t V, const int64_t* x, int64_t N, int64_t L, float* emb,
                   int* status, void* ws_hot, cudaStream_t st);
+int sif_select_frequent_rows(const int64_t* x, int64_t N, int64_t L, int64_t V, int k, void* ws_hot, int** ids_out,
+                             cudaStream_t st);
 }  // namespace mmb
 
 extern "C" size_t mmb_sif_embed_workspace_bytes(int64_t V, int d, int64_t N, int64_t L) {
@@ -864,6 +974,23 @@ int sif_embed_prescaled(const float* table, int64_t V, int d, const float* vocab
     sif_embed_warp_prefetch_kernel<3, 2, 4><<<grid, kEmbedWarps * 32, 0, st>>>(
         (const float4*)table, (int)V, d4, vocab_w, x, N, L, (float4*)emb, status, flags);
     MMB_LAUNCH_CHECK("sif_embed_general_standby");
+    return MMB_OK;
+  }
+  const int n_warm = option_embed_warm();
+  if (n_warm > 0 && d == 300 && V < ((int64_t)1 << kWarmRowBits) && N * L >= 64 * V) {
+    // L1 allocation policy per row: the K most frequent rows of a sample of the ids stay cacheable, the rest
+    // are read with L1::no_allocate
+    void* ws_hot = (void*)((char*)ws + 256 + (size_t)V * d * sizeof(float));
+    int* warm_ids = nullptr;
+    int rc = sif_select_frequent_rows(x, N, L, V, n_warm, ws_hot, &warm_ids, st);
+    if (rc) return rc;
+    sif_embed_prescaled_warm_kernel<3, 2, 4><<<grid, kEmbedWarps * 32, 0, st>>>(tp4, (int)V, d4, flags, warm_ids, n_warm,
+                                                                              x, N, L, (float4*)emb, status);
+    MMB_LAUNCH_CHECK("sif_embed_prescaled_warm");
+    sif_embed_warp_prefetch_kernel<3, 2, 4><<<grid, kEmbedWarps * 32, 0, st>>>(
+        (const float4*)table, (int)V, d4, vocab_w, x, N, L, (float4*)emb, status, flags);
+    MMB_LAUNCH_CHECK("sif_embed_general_standby");
+    note_kernel(0, "sif_embed_prescaled_warm_kernel<3,2,4>");
     return MMB_OK;
   }
   static const int variant = getenv("MMB_EMBED_PS_VARIANT") ? atoi(getenv("MMB_EMBED_PS_VARIANT")) : 0;

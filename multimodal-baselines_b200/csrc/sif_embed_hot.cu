@@ -10,7 +10,7 @@
 //      hot[d][u] = sum_k T'[hot_k][d] * count[k][u]        (T' = weight-scaled table, sif_embed.cu)
 // with integer counts -- exact in TF32 -- so it runs on tcgen05 (kind::tf32, T' split hi + lo: two passes,
 // 2^-22 relative per term) out of shared memory, while the warps gather only the remaining (cold) rows:
-//      setup   : a histogram of the first 32 k utterances' ids picks the 64 most frequent rows (device
+//      setup   : a histogram of the first 4096 utterances' ids picks the 64 most frequent rows (device
 //                side, deterministic); every CTA copies those rows of T' into shared memory in the
 //                canonical MN-major UMMA layout (SWIZZLE_128B, 32-byte atoms -- the layout of gram_tc.cu)
 //                and builds a 1024-slot hash of their ids
@@ -40,7 +40,7 @@ constexpr int kWarps = 32;
 constexpr int kThreads = kWarps * 32;
 constexpr int kSmemBytes = 2 * kABytes + kCBytes + kHashSize * 4 + kTileU * 4 + 64 + 1024 /*align*/;
 constexpr unsigned kEmpty = 0xffffffffu;
-constexpr int kSampleUtt = 32768;
+constexpr int kSampleUtt = 4096;      // x L tokens: enough to rank the head of the distribution, cheap in contended atomics
 
 __device__ __forceinline__ unsigned hashf(unsigned row) { return (row * 2654435761u) >> 22; }   // 10 bits
 
@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(256)
 // kK arg-max rounds run over a short shared-memory list instead of the V counters.
 constexpr int kMaxCand = 4096;
 __global__ void __launch_bounds__(1024)
-    hot_select_kernel(const int* __restrict__ counters, int V, int64_t n_sample, int* __restrict__ hot_ids) {
+    hot_select_kernel(const int* __restrict__ counters, int V, int64_t n_sample, int* __restrict__ hot_ids,
+                      int n_select = kK) {
   __shared__ long long cand[kMaxCand];          // (count << 32) | (0x7fffffff - id): max = highest count, lowest id
   __shared__ long long best_s[32];
   __shared__ int where_s[32];
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(1024)
   }
   __syncthreads();
   const int n = n_cand < kMaxCand ? n_cand : kMaxCand;
-  for (int r = 0; r < kK; ++r) {
+  for (int r = 0; r < n_select; ++r) {
     long long best = -1;
     int where = -1;
     for (int i = threadIdx.x; i < n; i += blockDim.x)
@@ -401,7 +402,25 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 }  // namespace hot
 
-size_t sif_embed_hot_extra_bytes(int64_t V) { return ((size_t)V * sizeof(int) + 255) / 256 * 256 + 256; }
+// sample histogram (V ints) + up to 512 selected row ids
+size_t sif_embed_hot_extra_bytes(int64_t V) { return ((size_t)V * sizeof(int) + 255) / 256 * 256 + 2048; }
+
+// The k (<= 512) most frequent rows among the first kSampleUtt utterances' ids -> ids_out (device, k ints, -1 padded).
+int sif_select_frequent_rows(const int64_t* x, int64_t N, int64_t L, int64_t V, int k, void* ws_hot, int** ids_out,
+                             cudaStream_t st) {
+  using namespace hot;
+  MMB_REQUIRE(k > 0 && k <= 512, "1..512 rows");
+  int* counters = (int*)ws_hot;
+  int* sel = (int*)((char*)ws_hot + ((size_t)V * sizeof(int) + 255) / 256 * 256);
+  MMB_CUDA(cudaMemsetAsync(counters, 0, (size_t)V * sizeof(int), st));
+  const int64_t n_sample = (N < kSampleUtt ? N : kSampleUtt) * L;
+  hot_hist_kernel<<<sm_count() * 4, 256, 0, st>>>(x, n_sample, (int)V, counters);
+  MMB_LAUNCH_CHECK("hot_hist");
+  hot_select_kernel<<<1, 1024, 0, st>>>(counters, (int)V, n_sample, sel, k);
+  MMB_LAUNCH_CHECK("hot_select");
+  *ids_out = sel;
+  return MMB_OK;
+}
 
 bool sif_embed_hot_eligible(int64_t V, int d, int64_t N, int64_t L) {
   if (option_embed_hot() == 0) return false;
@@ -412,14 +431,9 @@ bool sif_embed_hot_eligible(int64_t V, int d, int64_t N, int64_t L) {
 int sif_embed_hot(const float* tp, const int* flags, int64_t V, const int64_t* x, int64_t N, int64_t L, float* emb,
                   int* status, void* ws_hot, cudaStream_t st) {
   using namespace hot;
-  int* counters = (int*)ws_hot;
-  int* hot_ids = (int*)((char*)ws_hot + ((size_t)V * sizeof(int) + 255) / 256 * 256);
-  MMB_CUDA(cudaMemsetAsync(counters, 0, (size_t)V * sizeof(int), st));
-  const int64_t n_sample = (N < kSampleUtt ? N : kSampleUtt) * L;
-  hot_hist_kernel<<<sm_count() * 4, 256, 0, st>>>(x, n_sample, (int)V, counters);
-  MMB_LAUNCH_CHECK("hot_hist");
-  hot_select_kernel<<<1, 1024, 0, st>>>(counters, (int)V, n_sample, hot_ids);
-  MMB_LAUNCH_CHECK("hot_select");
+  int* hot_ids = nullptr;
+  int rc = sif_select_frequent_rows(x, N, L, V, kK, ws_hot, &hot_ids, st);
+  if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     MMB_CUDA(cudaFuncSetAttribute(sif_embed_hot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));

@@ -14,8 +14,9 @@ from _native import lib
 from oracle import sif_oracle as so
 
 
-def run(table, vw, ids, hot):
+def run(table, vw, ids, hot, warm=0):
     nv.check(lib.mmb_set_option(b'embed_hot', int(hot)))
+    nv.check(lib.mmb_set_option(b'embed_warm', int(warm)))
     n, L = ids.shape
     V, d = table.shape
     emb = torch.empty((n, d), dtype=torch.float32, device=ids.device)
@@ -61,6 +62,15 @@ def main():
         print('V=%d N=%d L=%d: %s %.3f ms | %s %.3f ms | hot vs gather %.2e, vs oracle: gather %.2e hot %.2e, '
               'deterministic %s -> %s' % (V, nn, L, k0, ms0, k1, ms1, err, e_or0, e_or1, torch.equal(hot, again),
                                           'ok' if good else 'FAIL'), flush=True)
+        if V == bench.VOCAB:
+            # L1 allocation policy per row (sif_embed_prescaled_warm_kernel): bit-identical results, fewer fabric bytes
+            for K in (64, 128, 160, 192, 256, 384):
+                w, stw, msw, kw = run(table, vw, ids, 0, K)
+                same = torch.equal(w, ref)
+                ok = ok and same and stw == 0 and 'warm' in kw
+                print('  warm K=%d: %s %.3f ms, identical to the plain pre-scaled kernel %s' % (K, kw, msw, same), flush=True)
+    nv.check(lib.mmb_set_option(b'embed_warm', 0))
+    nv.check(lib.mmb_set_option(b'embed_hot', 0))
     sys.exit(0 if ok else 1)
 
 
