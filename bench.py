@@ -139,16 +139,31 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_port_rate(table_np, weights_np, ids_np, repeats=1):
-    """The oracle port of the reference path (its own Python loops + sklearn) on host cores."""
+def reference_fn():
+    """(get_sentence_embeddings, kind, description): the reference's OWN sif.get_sentence_embeddings from
+    oracle/_ref (unmodified copies of its sif.py / sif_functions.py, made by oracle/make_ref.py where the reference
+    tree exists), else the oracle port with the reference's Python loops."""
+    from oracle import make_ref
     from oracle import sif_oracle as so
+    mod = make_ref.load()
+    if mod is not None:
+        return mod.get_sentence_embeddings, 'reference', ("the reference's own sif.get_sentence_embeddings "
+                                                          '(oracle/_ref: unmodified sif.py + sif_functions.py, Python loops '
+                                                          '+ sklearn TruncatedSVD)')
+    return so.get_sentence_embeddings_loop, 'port', ("oracle port of sif.py:84-94 with the reference's own Python loops "
+                                                     '+ sklearn TruncatedSVD')
+
+
+def cpu_port_rate(table_np, weights_np, ids_np, repeats=1):
+    """The reference path (its own Python loops + sklearn) on host cores."""
+    fn, kind, desc = reference_fn()
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        so.get_sentence_embeddings_loop(table_np, weights_np, ids_np)
+        fn(table_np, weights_np, ids_np)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return ids_np.shape[0] / best, best
+    return ids_np.shape[0] / best, best, kind, desc
 
 
 def cpu_threads():
@@ -162,7 +177,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    from oracle import sif_oracle as so
+    fn, kind, how = reference_fn()
     sample = int(os.environ.get('MMB_REF_SAMPLE', 20_000))     # same size as the GPU arm's cpu_baseline leg
     rng = np.random.default_rng(0)
     p = zipf_pmf(VOCAB)
@@ -176,21 +191,20 @@ def run_reference_arm(args):
     ids[np.arange(L_TOK)[None, :] >= lens] = 0
     ids = ids.astype(np.int64)
     for _ in range(args.warmup):
-        so.get_sentence_embeddings_loop(table, weights, ids)
+        fn(table, weights, ids)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        so.get_sentence_embeddings_loop(table, weights, ids)
+        fn(table, weights, ids)
     dt = (time.perf_counter() - t0) / args.steps
     value = sample / dt
     cores = cpu_threads()
-    desc = ('%d-utterance sample of the %s workload per step; oracle port of sif.py:84-94 with the '
-            "reference's own Python loops + sklearn TruncatedSVD" % (sample, WORKLOAD))
+    desc = '%d-utterance sample of the %s workload per step; %s' % (sample, WORKLOAD, how)
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'sample_utterances_per_step': sample},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': desc},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }), file=OUT, flush=True)
@@ -685,10 +699,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         sample = int(os.environ.get('MMB_CPU_SAMPLE', 20_000))
         sample = min(sample, n_local)
-        rate, secs = cpu_port_rate(table.cpu().numpy(), vocab_w.double().cpu().numpy(), ids[:sample].cpu().numpy())
-        cpu = {'value': rate, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'port',
-               'sample': 'first %d utterances of this workload, %.1f s; oracle port of sif.py:84-94 with the '
-                         "reference's Python loops + sklearn TruncatedSVD (BLAS threads = all cores)" % (sample, secs)}
+        rate, secs, kind, how = cpu_port_rate(table.cpu().numpy(), vocab_w.double().cpu().numpy(),
+                                              ids[:sample].cpu().numpy())
+        cpu = {'value': rate, 'unit': UNIT, 'cores': cpu_threads(), 'kind': kind,
+               'sample': 'first %d utterances of this workload, %.1f s; %s (BLAS threads = all cores)' % (sample, secs, how)}
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
         del ids

@@ -157,7 +157,7 @@ def test_bench_reference_arm_prints_one_json_line():
     assert len(lines) == 1, r.stdout[:500]
     line = json.loads(lines[0])
     assert line['impl'] == 'reference' and line['unit'] == 'utterances/s' and line['higher_is_better'] is True
-    assert line['value'] > 0 and line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['value'] > 0 and line['cpu_baseline']['kind'] in ('port', 'reference') and line['cpu_baseline']['cores'] >= 1
     assert line['e2e'] == {'value': line['value'], 'unit': line['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert line['gpu_launches'] == 0 and 'workload' in line['config']
 
