@@ -373,8 +373,11 @@ def verify_run(ctx):
         checks['pc_identical_on_all_ranks'] = {'ok': bool(all(torch.equal(pcs[0], q) for q in pcs))}
         if comm is not None:
             emb_n, pc_n, _ = mdist.sharded_sif_embedding(table, vocab_w, ids, N_UTT, lo, npc=1, comm=None)
+            # two FP32 summation orders of the ranks' Grams (rank order here, NCCL's ring / tree there): the
+            # components agree to ~1e-8 in cosine, the projected rows (small after the common direction is gone)
+            # to a few 1e-7 of their maxima at 2 ranks and ~1e-6 at 8 -- half the embedding tolerance is the bar
             checks['peer_exchange_vs_nccl'] = {'pc_cos': float(pc[0].double() @ pc_n[0].double()), 'min_cos': 1 - 1e-7,
-                                               'emb_err': rel_rows(emb, emb_n), 'tol': 1e-6}
+                                               'emb_err': rel_rows(emb, emb_n), 'tol': 5e-6}
             del emb_n
     # (5) the host-buffer (e2e) result against the device-resident one (Gram summed per chunk: different
     #     FP32 order, same tolerance as the embeddings)
@@ -399,9 +402,16 @@ def verify_run(ctx):
     for c in checks.values():
         c['ok'] = passed(c)
     flag = torch.tensor([0 if all(c['ok'] for c in checks.values()) else 1], device=dev)
+    failed = {}
     if world > 1:
         dist.all_reduce(flag)
-    return {'ok': int(flag.item()) == 0, 'rank0': checks, 'ranks_failed': int(flag.item())}
+        mine = {k: c for k, c in checks.items() if not c['ok']}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)           # which check failed on which rank, for the line
+        failed = {'rank%d' % r: g for r, g in enumerate(gathered) if g}
+    else:
+        failed = {'rank0': {k: c for k, c in checks.items() if not c['ok']}} if int(flag.item()) else {}
+    return {'ok': int(flag.item()) == 0, 'rank0': checks, 'ranks_failed': int(flag.item()), 'failed': failed}
 
 
 def mmb_secondary(steps=50):

@@ -23,11 +23,17 @@ def mods():
     return torch, losses, models
 
 
+_ERRLOG = os.environ.get('MMB_TEST_ERRLOG')      # path: every close() appends (name, err, rtol) -- how tolerances are set
+
+
 def close(got, want, rtol, name=''):
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
     assert got.shape == want.shape, (name, got.shape, want.shape)
     scale = max(np.abs(want).max(), 1e-12)
     err = np.abs(got - want).max() / scale
+    if _ERRLOG:
+        with open(_ERRLOG, 'a') as fh:
+            fh.write('%s\t%.3e\t%.1e\t%s\n' % (name, err, rtol, os.environ.get('PYTEST_CURRENT_TEST', '')))
     assert err < rtol, (name, err)
 
 

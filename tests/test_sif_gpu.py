@@ -561,3 +561,48 @@ def test_prescaled_table_path_equals_general_kernel(mods):
     assert stb & nv.STATUS_BAD_INDEX
     # too small a batch: no scratch requested, plain kernel
     assert lib.mmb_sif_embed_workspace_bytes(V, d, 10, L) == 0
+
+
+def test_embed_experimental_paths_are_correct(mods):
+    """The two round-2 experiments on the embed kernel stay selectable (mmb_set_option) and correct: the
+    tensor-core hot-row path (tcgen05 kind::tf32 over the 64 most frequent rows) and the per-row L1 allocation
+    policy.  Neither is the default (both measured slower)."""
+    import torch
+    nv, sf, sif = mods
+    lib = nv.lib
+    dev = torch.device('cuda')
+    rng = np.random.default_rng(21)
+    V, d, n, L = 2000, 300, 4500, 64
+    We = cases.table(V, d, seed=5)
+    ids, p = cases.zipf_ids(rng, n, L, V)
+    ids[9, 4] = -3
+    weights = cases.sif_weights(p).astype(np.float32)
+    t_We, t_w, t_ids = torch.tensor(We, device=dev), torch.tensor(weights, device=dev), torch.tensor(ids, device=dev)
+
+    def run():
+        emb = torch.empty((n, d), dtype=torch.float32, device=dev)
+        st = torch.zeros(1, dtype=torch.int32, device=dev)
+        nbytes = lib.mmb_sif_embed_workspace_bytes(V, d, n, L)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        nv.check(lib.mmb_sif_embed_ws(nv.ptr(t_We), V, d, nv.ptr(t_w), nv.ptr(t_ids), n, L, nv.ptr(emb), nv.ptr(st),
+                                      nv.ptr(ws), nbytes, nv.stream_ptr()))
+        assert int(st.item()) == 0
+        return emb, (lib.mmb_last_kernel(0) or b'').decode()
+    try:
+        ref, k0 = run()
+        assert 'prescaled_kernel' in k0
+        nv.check(lib.mmb_set_option(b'embed_warm', 128))
+        warm, k1 = run()
+        assert 'warm' in k1 and torch.equal(warm, ref)               # only the cache policy differs
+        nv.check(lib.mmb_set_option(b'embed_warm', 0))
+        nv.check(lib.mmb_set_option(b'embed_hot', 1))
+        hot, k2 = run()
+        assert 'hot' in k2
+        assert rel_err(hot.double().cpu().numpy(), ref.double().cpu().numpy()) < 5e-6
+        w = so.seq2weight(ids, np.ones(ids.shape), weights.astype(np.float64))
+        assert rel_err(hot.double().cpu().numpy(), so.get_weighted_average(We, ids, w)) < EMB_RTOL
+        with pytest.raises(ValueError):
+            nv.check(lib.mmb_set_option(b'no_such_option', 1))
+    finally:
+        lib.mmb_set_option(b'embed_warm', 0)
+        lib.mmb_set_option(b'embed_hot', 0)
