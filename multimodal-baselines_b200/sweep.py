@@ -129,9 +129,11 @@ class Prepared(object):
         return self.by_pos[pos_embed_dim]
 
 
-def run_config(cfg, prep, epochs_scale=1.0, cuda_graph=True, verbose=False):
+def run_config(cfg, prep, epochs_scale=1.0, cuda_graph=True, verbose=False, defer_regressor=False):
     """One grid point, reference simplesif.py:625-914 (e2e branch).  Returns the test metrics of
-    the downstream regressor and the final losses."""
+    the downstream regressor and the final losses.  ``defer_regressor``: stop after the latent phases and
+    return the regressor problem as a ``sentiment_batched.RegressorJob`` under ``'job'`` (with the random
+    stream captured where the regressor would start), to be trained together with other grid points'."""
     import simplesif
     from models import AudioVisualGeneratorMultimodal
     from sentiment_model import SentimentData, SentimentModel, train_sentiment_for_latents
@@ -175,6 +177,15 @@ def run_config(cfg, prep, epochs_scale=1.0, cuda_graph=True, verbose=False):
                                                                   loaders[2], args['n_epochs'], args['lr'], word_fn,
                                                                   device, verbose=False)
         lap('valid_test_latents')
+        if defer_regressor:
+            import sentiment_batched
+            if sentiment_batched.can_batch(args, prep.labels):
+                job = sentiment_batched.RegressorJob(args, (train_embed, valid_embed, test_embed), tuple(prep.labels),
+                                                     tag=cfg['config_num'])
+                phase['graph_capture_latent_loops'] = simplesif.CAPTURE_SECONDS[0] - cap0
+                sys.stdout = old_stdout
+                return {'config_num': cfg['config_num'], 'job': job, 'train_loss': train_losses[-1],
+                        'test_loss': test_losses[-1], 'phase_s': {k: round(v, 3) for k, v in phase.items()}}
         results, _ = train_sentiment_for_latents(args, (train_embed, valid_embed, test_embed), tuple(prep.labels),
                                                  device)
         lap('sentiment_regressor')
@@ -197,6 +208,9 @@ def main(argv=None):
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--only', type=int, nargs='*', default=None, help='run just these config numbers')
     ap.add_argument('--out', default='')
+    ap.add_argument('--regressor-batch', type=int, default=8,
+                    help='train the downstream regressors of this many grid points as one batched model '
+                         '(SURVEY 8f N4; 1 = the sequential module per grid point)')
     a = ap.parse_args(argv)
     import torch.distributed as dist
     world, rank = int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('RANK', 0))
@@ -231,7 +245,31 @@ def main(argv=None):
         sys.stdout = old
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    out = [run_config(cfg, prep, a.epochs_scale, not a.no_graph) for cfg in mine]
+    out = []
+    if a.regressor_batch > 1:
+        import sentiment_batched
+        for o in range(0, len(mine), a.regressor_batch):
+            part = [run_config(cfg, prep, a.epochs_scale, not a.no_graph, defer_regressor=True)
+                    for cfg in mine[o:o + a.regressor_batch]]
+            jobs = [r['job'] for r in part if 'job' in r]
+            t_reg = time.perf_counter()
+            buf, old_stdout = open(os.devnull, 'w'), sys.stdout
+            sys.stdout = buf                         # the metric helpers print reports
+            try:
+                sentiment_batched.run_jobs(jobs, device, max_batch=a.regressor_batch)
+            finally:
+                sys.stdout = old_stdout
+            torch.cuda.synchronize()
+            t_reg = (time.perf_counter() - t_reg) / max(len(jobs), 1)
+            for r in part:
+                job = r.pop('job', None)
+                if job is not None:
+                    r['results'] = {k: v for k, v in job.results.items()
+                                    if k in ('mae', 'accuracy', 'corr', 'mult_acc', 'f_score')}
+                    r['phase_s']['sentiment_regressor_batched_share'] = round(t_reg, 3)
+            out.extend(part)
+    else:
+        out = [run_config(cfg, prep, a.epochs_scale, not a.no_graph) for cfg in mine]
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if world > 1:
@@ -252,6 +290,7 @@ def main(argv=None):
                           'processes_per_gpu': max(1, world // max(n_dev, 1)), 'seconds': dt, 'value': len(out) / dt,
                           'value_per_gpu': len(out) / dt / max(1, min(world, n_dev)),
                           'epochs_scale': a.epochs_scale, 'cuda_graph': not a.no_graph,
+                          'regressor_batch': a.regressor_batch,
                           'diverged': [r['config_num'] for r in out if r.get('diverged')],
                           'best_test_MAE': (min(maes) if maes else None)}), flush=True)
 

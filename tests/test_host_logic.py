@@ -310,3 +310,41 @@ def test_loaders_read_the_reference_file_layout(tmp_path, monkeypatch):
         v, t = utils.load_text_ids('pom', ref_root, ('valid', 'test'))
         assert v.shape == (100, 1089) and t.shape == (203, 1357) and t.dtype == np.int64
         assert max(utils.load_word2ix('mosi', ref_root).values()) == 3015
+
+
+def test_batched_regressors_equal_sequential_ones(capsys):
+    """K grid points' downstream regressors trained as ONE batched model (sentiment_batched) give the
+    metrics, loss curves and random-stream position of K sequential train_sentiment_for_latents runs -- same
+    initialisation and shuffles per config (the generator is replayed from where each run would start), different
+    step sizes per config.  CPU here (plain torch both ways); the GPU test repeats it with graph replay."""
+    import torch
+    import sentiment_model
+    import sentiment_batched
+    jobs, want = [], []
+    for k, (seed, lr) in enumerate([(11, 0.1), (12, 0.01), (13, 0.05)]):
+        args, lat, labs = cases.sentiment_inputs(dataset='mosi', n_out=1, early_stopping=False, seed=81 + k)
+        args = dict(args, sentiment_lr=lr, n_sentiment_epochs=25)
+        lat_t = tuple(torch.tensor(x) for x in lat)
+        torch.manual_seed(seed)
+        torch.rand(3)                                          # the stream is somewhere in the middle, as after latent loops
+        state = torch.get_rng_state()
+        res, (tl, vl) = sentiment_model.train_sentiment_for_latents(args, lat_t, tuple(labs), torch.device('cpu'))
+        want.append((res, tl, vl, torch.get_rng_state()))
+        jobs.append(sentiment_batched.RegressorJob(args, lat_t, tuple(labs), rng_state=state))
+    assert all(sentiment_batched.can_batch(j.args, j.labels) for j in jobs)
+    sentiment_batched.run_jobs(jobs, torch.device('cpu'))
+    capsys.readouterr()
+    for job, (res, tl, vl, final_state) in zip(jobs, want):
+        for k in ('mae', 'corr', 'mult_acc', 'f_score', 'accuracy'):
+            np.testing.assert_allclose(np.asarray(job.results[k], dtype=np.float64), np.asarray(res[k], dtype=np.float64),
+                                       rtol=0, atol=1e-5, err_msg=k)
+        np.testing.assert_allclose(job.train_losses, tl, rtol=1e-5)
+        np.testing.assert_allclose(job.valid_losses, vl, rtol=1e-5)
+        assert torch.equal(job.final_rng_state, final_state)   # exactly the draws the sequential run makes
+    # (N, 1) labels and early stopping stay with the sequential module
+    args, lat, labs = cases.sentiment_inputs(**cases.SENTIMENT_CASES['mosi_column_labels'])
+    assert not sentiment_batched.can_batch(args, labs)
+    args, lat, labs = cases.sentiment_inputs(**cases.SENTIMENT_CASES['mosi_early_stopping'])
+    assert not sentiment_batched.can_batch(args, labs)
+    args, lat, labs = cases.sentiment_inputs(**cases.SENTIMENT_CASES['pom'])
+    assert sentiment_batched.can_batch(args, labs)

@@ -512,3 +512,17 @@ def test_sweep_grid_point_equals_run_experiment(mods, config_num, capsys):
     for k in ('mae', 'corr', 'accuracy', 'mult_acc', 'f_score'):
         np.testing.assert_allclose(np.asarray(got['results'][k], dtype=np.float64),
                                    np.asarray(results[k], dtype=np.float64), rtol=0, atol=1e-6, err_msg=k)
+    # the same grid point with its regressor deferred and trained as part of a batched model (here
+    # together with a second point that differs in the regressor's step size) -- same latents, same shuffles and
+    # initialisation, batched GEMMs instead of per-config ones: MAE / correlation to the third decimal
+    import sentiment_batched
+    cfg2 = dict(cfg, sentiment_lr=0.01 if cfg['sentiment_lr'] == 0.1 else 0.1)
+    parts = [sweep.run_config(c, prep, epochs_scale=scale, defer_regressor=True) for c in (cfg, cfg2)]
+    assert all('job' in r for r in parts)
+    sentiment_batched.run_jobs([r['job'] for r in parts], dev)
+    capsys.readouterr()
+    assert abs(parts[0]['train_loss'] - got['train_loss']) <= 1e-6 * abs(got['train_loss'])
+    for k in ('mae', 'corr'):
+        assert abs(float(parts[0]['job'].results[k]) - float(got['results'][k])) < 1e-3, k
+    assert abs(float(parts[0]['job'].results['accuracy']) - float(got['results']['accuracy'])) <= 1.5 / 90
+    assert float(parts[1]['job'].results['mae']) != float(parts[0]['job'].results['mae'])      # its own step size
