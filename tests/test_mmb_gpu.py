@@ -10,8 +10,13 @@ from oracle import mmb_oracle as mo
 
 pytestmark = pytest.mark.gpu
 
-VAL_RTOL = 1e-4      # FP32 kernels vs the reference's FP32 torch ops (different summation order)
-GRAD_RTOL = 2e-3     # relative to the largest entry of the gradient tensor
+# Tolerances = about 10x the largest error any check of that class shows on B200 (MMB_TEST_ERRLOG=path records
+# every close(): values <= 1.2e-6, gradients and loop results <= 3.7e-6 of the tensor's largest entry -- FP32
+# kernels against the reference's FP32 torch ops, different summation order, nothing worse; the acos' singularity
+# at |cos| -> 1 is not reached by any fixture).  Round 1 had 1e-4 / 2e-3 here without having measured.
+VAL_RTOL = 1e-5
+GRAD_RTOL = 4e-5     # relative to the largest entry of the gradient tensor
+LOOP_RTOL = 5e-5     # latents / weights / losses after a few epochs of the optimisation loops
 
 
 @pytest.fixture(scope='module')
@@ -178,7 +183,7 @@ def test_word_term_ids_long_transcripts(mods):
         res.append((lp.detach(), lat.grad.clone()))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])          # deterministic
     close(res[0][0].cpu(), res[2][0].cpu(), 1e-5, 'lp ids vs dense')
-    close(res[0][1].cpu(), res[2][1].cpu(), 2e-4, 'grad ids vs dense')
+    close(res[0][1].cpu(), res[2][1].cpu(), GRAD_RTOL, 'grad ids vs dense')
     bad = ids.clone()
     bad[3, 7] = V + 5
     st = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -301,9 +306,9 @@ def test_optimize_latents_matches_reference_loop(mods, golden_dir, tag):
     emb, (losses_, _) = simplesif.optimize_latents(dict(cfg['args']), cfg['train'], model, c['latents'], loader,
                                                    cfg['epochs'], cfg['lr'], word_fn, dev, verbose=False)
     assert emb.shape == c['latents'].shape and not emb.requires_grad
-    close(np.array(losses_), g[tag + '_losses'], 2e-4, 'losses')
-    close(emb.cpu(), g[tag + '_emb'], 1e-3, 'latents')
-    close(model.embed2out['audio']['mu'].weight.detach().cpu(), g[tag + '_Wmu_audio'], 1e-3, 'W')
+    close(np.array(losses_), g[tag + '_losses'], LOOP_RTOL, 'losses')
+    close(emb.cpu(), g[tag + '_emb'], LOOP_RTOL, 'latents')
+    close(model.embed2out['audio']['mu'].weight.detach().cpu(), g[tag + '_Wmu_audio'], LOOP_RTOL, 'W')
 
 
 @pytest.mark.parametrize('tag', sorted(cases.OPT_CASES))
@@ -340,9 +345,9 @@ def test_cuda_graph_step_matches_eager_loop(mods, golden_dir, tag, shuffle):
 
     emb_g, ls_g, W_g = run(True)
     if not shuffle:
-        close(ls_g, g[tag + '_losses'], 2e-4, 'losses')
-        close(emb_g, g[tag + '_emb'], 1e-3, 'latents')
-        close(W_g, g[tag + '_Wmu_audio'], 1e-3, 'W')
+        close(ls_g, g[tag + '_losses'], LOOP_RTOL, 'losses')
+        close(emb_g, g[tag + '_emb'], LOOP_RTOL, 'latents')
+        close(W_g, g[tag + '_Wmu_audio'], LOOP_RTOL, 'W')
     emb_s, ls_s, W_s = run('step')          # one graph per step instead of one per epoch: the same kernels
     close(ls_g, ls_s, 1e-6, 'losses, epoch graph vs step graphs')
     close(emb_g, emb_s, 1e-6, 'latents, epoch graph vs step graphs')
@@ -451,10 +456,10 @@ def test_downstream_metrics(mods, golden_dir, tag, graph, text_ids, capsys):
     close(cases.checksum(np.concatenate([We.ravel()] + [np.asarray(s['covarep']).ravel() for s in splits])),
           g[tag + '_inputs_sum'], 1e-9, 'inputs')
     # the intermediate latents first: a drift here explains any metric difference below
-    close(train_losses, g[tag + '_train_losses'], 1e-3, 'train_losses')
-    close(train_e[:8].cpu().numpy(), g[tag + '_train_embed'], 2e-3, 'train_embed')
-    close(test_e[:8].cpu().numpy(), g[tag + '_test_embed'], 2e-3, 'test_embed')
-    close(cases.checksum(test_e.cpu().numpy())[1], g[tag + '_test_embed_sum'][1], 1e-3, 'test_embed_sum')
+    close(train_losses, g[tag + '_train_losses'], 1e-4, 'train_losses')
+    close(train_e[:8].cpu().numpy(), g[tag + '_train_embed'], 1e-4, 'train_embed')
+    close(test_e[:8].cpu().numpy(), g[tag + '_test_embed'], 1e-4, 'test_embed')
+    close(cases.checksum(test_e.cpu().numpy())[1], g[tag + '_test_embed_sum'][1], 1e-4, 'test_embed_sum')
     for k in ('mae', 'corr'):
         got, want = np.asarray(results[k], dtype=np.float64), g['%s_after_%s' % (tag, k)]
         assert got.shape == want.shape
@@ -526,3 +531,34 @@ def test_sweep_grid_point_equals_run_experiment(mods, config_num, capsys):
         assert abs(float(parts[0]['job'].results[k]) - float(got['results'][k])) < 1e-3, k
     assert abs(float(parts[0]['job'].results['accuracy']) - float(got['results']['accuracy'])) <= 1.5 / 90
     assert float(parts[1]['job'].results['mae']) != float(parts[0]['job'].results['mae'])      # its own step size
+
+
+@pytest.mark.parametrize('tag', sorted(cases.OPT_CASES))
+def test_data_parallel_loop_single_rank_matches_reference_loop(mods, golden_dir, tag):
+    """mmb_dp.optimize_latents_dp (SURVEY 8e "MMB training") with ONE rank -- no process group, every exchange a
+    no-op -- must still be the reference loop: global-batch mean as sum / B, flat head-gradient buffer,
+    SyncBatchNormFunction in place of nn.BatchNorm1d.  (Two and eight ranks: tools/dp_check.py, run by
+    tests/test_dist_gpu.py on multi-GPU boxes and by bench.py at every N > 1.)"""
+    torch, losses, models = mods
+    import mmb_dp
+    import simplesif
+    import utils
+    from torch.utils.data import DataLoader
+    g = np.load(os.path.join(golden_dir, 'optimize_latents.npz'))
+    cfg = cases.OPT_CASES[tag]
+    c = cases.mmb_inputs(**cfg['inputs'])
+    dev = torch.device('cuda')
+    model = models.AudioVisualGeneratorMultimodal(c['d'], c['A'], c['Vd'], norm=cfg['inputs']['norm'],
+                                                  frozen_weights=False, unimodal=cfg['inputs']['unimodal']).to(dev)
+    cases.load_heads(model, c['heads'], c.get('norm_params'))
+    ds = utils.MMData(c['text'], c['aud'], c['vis'], {'text': c['text_m'], 'covarep': c['aud_m'],
+                                                       'facet': c['vis_m']}, c['text_w'], dev)
+    n = c['latents'].shape[0]
+    index_loader = DataLoader(range(n), batch_size=cfg['batch'], shuffle=False)
+    We_t = torch.tensor(c['We'], device=dev)
+    word_fn = simplesif.make_word_log_prob_fn({'word_sim_metric': 'angular'}, None, We_t)
+    emb, (losses_, _) = mmb_dp.optimize_latents_dp(dict(cfg['args']), cfg['train'], model, c['latents'], ds, index_loader,
+                                                   cfg['epochs'], cfg['lr'], word_fn, dev, 0, comm=None, verbose=False)
+    close(np.array(losses_), g[tag + '_losses'], LOOP_RTOL, 'losses')
+    close(emb.cpu(), g[tag + '_emb'], LOOP_RTOL, 'latents')
+    close(model.embed2out['audio']['mu'].weight.detach().cpu(), g[tag + '_Wmu_audio'], LOOP_RTOL, 'W')
