@@ -148,7 +148,7 @@ def reference_fn():
     mod = make_ref.load()
     if mod is not None:
         return mod.get_sentence_embeddings, 'reference', ("the reference's own sif.get_sentence_embeddings "
-                                                          '(oracle/_ref: unmodified sif.py + sif_functions.py, Python loops '
+                                                          '(oracle/_ref/reference_sif.zip: its unmodified sif.py + sif_functions.py, Python loops '
                                                           '+ sklearn TruncatedSVD)')
     return so.get_sentence_embeddings_loop, 'port', ("oracle port of sif.py:84-94 with the reference's own Python loops "
                                                      '+ sklearn TruncatedSVD')
