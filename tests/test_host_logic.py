@@ -348,3 +348,35 @@ def test_batched_regressors_equal_sequential_ones(capsys):
     assert not sentiment_batched.can_batch(args, labs)
     args, lat, labs = cases.sentiment_inputs(**cases.SENTIMENT_CASES['pom'])
     assert sentiment_batched.can_batch(args, labs)
+
+
+def test_bench_refuses_a_stale_ncu_record(tmp_path, monkeypatch):
+    """roofline.traffic was multiplied out of an ncu capture of a DIFFERENT kernel instantiation.
+    bench.py now takes the kernel name from the library's dispatch and uses the committed capture only when ncu
+    saw the same instantiation (template arguments included, whatever the spelling)."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    bench = importlib.import_module('bench')
+    n = bench.norm_kernel_name
+    assert n('void mmb::sif_embed_warp_kernel<3, 0, 2, 4, 0>(const float4 *, int, int)') == \
+        n('sif_embed_warp_kernel<3,false,2,4,false>') == 'sif_embed_warp_kernel<3,0,2,4,0>'
+    assert n('void sif_embed_prescaled_kernel<3, 2, 4>(const float4 *, int, int, const int *)') == \
+        n('sif_embed_prescaled_kernel<3,2,4>')
+    assert n('sif_embed_prescaled_kernel<3,2,4>') != n('sif_embed_warp_prefetch_kernel<3,2,4>')
+    (tmp_path / 'profiles').mkdir()
+    rec = {'zipf': {'ncu_kernel_name': 'void sif_embed_warp_kernel<3, 0, 2, 4, 0>(const float4 *)',
+                    'dram_bytes_per_utterance': 7458.0, 'source': 'x'}}
+    json.dump(rec, open(tmp_path / 'profiles' / 'embed_traffic.json', 'w'))
+    monkeypatch.setattr(bench, 'ROOT', str(tmp_path))
+    got, why = bench.load_ncu_record('sif_embed_prescaled_kernel<3,2,4>', 'zipf')
+    assert got is None and 'stale capture' in why
+    got, why = bench.load_ncu_record('sif_embed_warp_kernel<3,false,2,4,false>', 'zipf')
+    assert got is not None and got['dram_bytes_per_utterance'] == 7458.0
+    got, why = bench.load_ncu_record('sif_embed_warp_kernel<3,false,2,4,false>', 'uniform')
+    assert got is None and 'no uniform record' in why
+    # the committed record matches the kernel the library dispatches for the bench workload
+    monkeypatch.setattr(bench, 'ROOT', root)
+    got, why = bench.load_ncu_record('sif_embed_prescaled_kernel<3,2,4>', 'zipf')
+    assert got is not None, why
