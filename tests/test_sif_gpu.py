@@ -606,3 +606,33 @@ def test_embed_experimental_paths_are_correct(mods):
     finally:
         lib.mmb_set_option(b'embed_warm', 0)
         lib.mmb_set_option(b'embed_hot', 0)
+
+
+def test_ragged_equals_padded_at_bench_shape(mods):
+    """Size-independent property at the bench shape (64 tokens, 400 k vocabulary, 200 k utterances): the CSR path
+    (padded -> lengths -> offsets -> compacted tokens -> mmb_sif_embed_ragged) gives the padded path's averages, the
+    conversion is lossless, the offsets are the exclusive scan of the lengths, and an empty batch is a no-op."""
+    import torch
+    nv, sf, sif = mods
+    dev = torch.device('cuda')
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    V, d, n, L = 400_000, 300, 200_000, 64
+    table = 0.4 * torch.randn((V, d), device=dev, generator=g) + 0.3 * torch.randn((1, d), device=dev, generator=g)
+    ids = (torch.rand((n, L), device=dev, generator=g).pow(6.0) * (V - 1)).long() + 1
+    lens = torch.randint(0, L + 1, (n, 1), device=dev, generator=g)          # includes empty utterances
+    ids[torch.arange(L, device=dev)[None, :] >= lens] = 0
+    vw = torch.rand(V, device=dev, generator=g) * 0.9 + 0.1
+    vw[0] = 1.0
+    rag = sf.to_ragged(ids)
+    assert torch.equal(rag.lengths(), lens[:, 0])
+    assert torch.equal(rag.offsets, torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), lens[:, 0].cumsum(0)]))
+    assert torch.equal(rag.to_padded(), ids)
+    a = sf.sif_embedding_ragged(table, vw, rag, npc=0)
+    b = sf.sif_embedding_device(table, vw, ids, npc=0)
+    assert rel_err(a.double().cpu().numpy(), b.double().cpu().numpy()) < 2e-6
+    a2 = sf.sif_embedding_ragged(table, vw, rag, npc=0)
+    assert torch.equal(a, a2)                                                  # deterministic
+    empty = sf.to_ragged(torch.zeros((0, L), dtype=torch.int64, device=dev))
+    assert empty.shape == (0, L) and int(empty.tokens.numel()) == 0
+    assert sf.sif_embedding_ragged(table, vw, empty, npc=0).shape == (0, d)
