@@ -600,26 +600,31 @@ def main():
         d_tmp_o = torch.empty((n_local, DIM), dtype=torch.float32, device=dev)
         hi_t, ho_t = torch.as_tensor(h_ids.array), torch.as_tensor(h_out.array)
         d_tmp_i.copy_(hi_t, non_blocking=True)
-        barrier()
-        t0 = time.perf_counter()
-        d_tmp_i.copy_(hi_t, non_blocking=True)
-        torch.cuda.synchronize()
-        t_h2d = time.perf_counter() - t0
-        barrier()
-        t0 = time.perf_counter()
         ho_t.copy_(d_tmp_o, non_blocking=True)
-        torch.cuda.synchronize()
-        t_d2h = time.perf_counter() - t0
-        tt = torch.tensor([t_h2d, t_d2h], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        best = None
+        for _rep in range(3):                     # max over ranks per repetition, best repetition
+            barrier()
+            t0 = time.perf_counter()
+            d_tmp_i.copy_(hi_t, non_blocking=True)
+            torch.cuda.synchronize()
+            t_h2d = time.perf_counter() - t0
+            barrier()
+            t0 = time.perf_counter()
+            ho_t.copy_(d_tmp_o, non_blocking=True)
+            torch.cuda.synchronize()
+            t_d2h = time.perf_counter() - t0
+            cur = torch.tensor([t_h2d, t_d2h], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(cur, op=dist.ReduceOp.MAX)
+            best = cur if best is None else torch.minimum(best, cur)
+        tt = best
         ceil_s = float(tt.sum().item())
         e2e['copy_ceiling'] = {'h2d_ms': float(tt[0].item()) * 1e3, 'd2h_ms': float(tt[1].item()) * 1e3,
                                'h2d_gbs_aggregate': N_UTT * L_TOK * 8 / float(tt[0].item()) / 1e9,
                                'd2h_gbs_aggregate': N_UTT * DIM * 4 / float(tt[1].item()) / 1e9,
                                'value': N_UTT / ceil_s, 'frac': (N_UTT / float(dt.item())) / (N_UTT / ceil_s),
                                'how': 'H2D of the ids then D2H of the embeddings on the same pinned buffers, all ranks '
-                                      'at once, max over ranks, no compute; numa: %s' % mdist.numa_note()}
+                                      'at once, max over ranks, best of 3, no compute; numa: %s' % mdist.numa_note()}
         del d_tmp_i, d_tmp_o
         h_ids.free()
         h_out.free()
