@@ -636,3 +636,41 @@ def test_ragged_equals_padded_at_bench_shape(mods):
     empty = sf.to_ragged(torch.zeros((0, L), dtype=torch.int64, device=dev))
     assert empty.shape == (0, L) and int(empty.tokens.numel()) == 0
     assert sf.sif_embedding_ragged(table, vw, empty, npc=0).shape == (0, d)
+
+
+def test_full_size_properties_10M(mods):
+    """BASELINE configs[3] at FULL size (10 M utterances x 64 tokens, 400 k vocabulary, d = 300) through the composed
+    device call: bitwise determinism, every output row orthogonal to the removed component, the component a unit
+    vector with sklearn's sign rule, and sampled rows (first, last, and 62 in between) equal to the NumPy oracle's
+    weighted average projected with that component.  (bench.py's `verify` block repeats this at every GPU count.)"""
+    import torch
+    import bench
+    nv, sf, sif = mods
+    dev = torch.device('cuda')
+    free, _total = torch.cuda.mem_get_info()
+    if free < 60 * (1 << 30):
+        pytest.skip('needs ~45 GB of device memory')
+    n, L, V, d = 10_000_000, 64, 400_000, 300
+    table, vw, p = bench.make_table_and_weights(dev, V=V, d=d)
+    ids = bench.make_ids(dev, n, L, p, seed=2024)
+    emb, pc = sf.sif_embedding_device(table, vw, ids, npc=1, return_pc=True)
+    emb2, pc2 = sf.sif_embedding_device(table, vw, ids, npc=1, return_pc=True)
+    assert torch.equal(pc, pc2) and torch.equal(emb, emb2)
+    del emb2
+    assert abs(float(pc.double().norm()) - 1.0) < 1e-6
+    assert float(pc[0, pc[0].abs().argmax()]) > 0                                  # svd_flip(u_based_decision=False)
+    worst = 0.0
+    for s0 in range(0, n, 1 << 21):
+        blk = emb[s0:s0 + (1 << 21)]
+        worst = max(worst, float((blk @ pc[0]).abs().max()) / float(blk.abs().max()))
+    assert worst < 1e-4
+    rows = torch.cat([torch.tensor([0, n - 1]), torch.randint(1, n - 1, (62,), generator=torch.Generator().manual_seed(1))]).to(dev)
+    ids_s = ids[rows]
+    uniq, inv = torch.unique(ids_s, return_inverse=True)                            # a small table of the rows they touch
+    We_s = table[uniq].cpu().numpy()
+    w_s = vw[uniq].double().cpu().numpy()
+    ids_np = inv.cpu().numpy()
+    w = so.seq2weight(ids_np, np.ones(ids_np.shape), w_s)
+    avg = so.get_weighted_average(We_s, ids_np, w)
+    want = so.remove_pc_with(avg, pc.double().cpu().numpy())
+    assert rel_err(emb[rows].double().cpu().numpy(), want) < EMB_RTOL
