@@ -255,7 +255,11 @@ def get_log_prob_matrix(args, latents, out, data, masks, word_log_prob_fn,
         print({m: float(lp[i].min()) for i, m in enumerate(names)}, float(word_log_prob.min()))
 
     # the combination of lines 267-272 as one launch each way (mmb_combine_lp) instead of sum / mul / mul / add
-    if 'word_loss_weight' in args:
+    if args.get('_loss_weights_dev') is not None:
+        # (other_weight, word_weight) as one-element device tensors: GraphedStep in step-cache mode (sweep.py re-uses a
+        # captured step for grid points that differ only in these weights); same float32 values, read by the kernel
+        other_weight, word_weight = args['_loss_weights_dev']
+    elif 'word_loss_weight' in args:
         word_weight = args['word_loss_weight']
         other_weight = (1. - word_weight) / len(names)
     else:

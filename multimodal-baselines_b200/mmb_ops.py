@@ -236,22 +236,26 @@ class CombineLPFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, lp, wlp, other_w, word_w):
+        """``other_w`` / ``word_w``: Python numbers, or one-element float32 CUDA tensors -- the kernel then reads the
+        weights from device memory, so a captured graph serves every grid point's weights (sweep.py)."""
         lp, wlp = _f32(lp), _f32(wlp)
         M, B = lp.shape
         out = torch.empty(B, dtype=torch.float32, device=lp.device)
-        nv.check(lib.mmb_combine_lp(nv.ptr(lp), nv.ptr(wlp), M, B, float(other_w), float(word_w), None, None,
-                                    nv.ptr(out), nv.stream_ptr()))
-        ctx.w = (float(other_w), float(word_w), M, B)
+        dev_w = torch.is_tensor(other_w)
+        ow, ww = (0., 0.) if dev_w else (float(other_w), float(word_w))
+        nv.check(lib.mmb_combine_lp(nv.ptr(lp), nv.ptr(wlp), M, B, ow, ww, nv.ptr(other_w) if dev_w else None,
+                                    nv.ptr(word_w) if dev_w else None, nv.ptr(out), nv.stream_ptr()))
+        ctx.w = (ow, ww, M, B, other_w if dev_w else None, word_w if dev_w else None)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        ow, ww, M, B = ctx.w
+        ow, ww, M, B, ow_t, ww_t = ctx.w
         g = _f32(g)
         g_lp = torch.empty((M, B), dtype=torch.float32, device=g.device)
         g_wlp = torch.empty(B, dtype=torch.float32, device=g.device)
-        nv.check(lib.mmb_combine_lp_backward(nv.ptr(g), M, B, ow, ww, None, None, nv.ptr(g_lp), nv.ptr(g_wlp),
-                                             nv.stream_ptr()))
+        nv.check(lib.mmb_combine_lp_backward(nv.ptr(g), M, B, ow, ww, nv.ptr(ow_t), nv.ptr(ww_t), nv.ptr(g_lp),
+                                             nv.ptr(g_wlp), nv.stream_ptr()))
         return g_lp, g_wlp, None, None
 
 

@@ -227,6 +227,35 @@ class GraphedStep(object):
         self.fork = str(args.get('graph_fork', os.environ.get('MMB_GRAPH_FORK', '1'))) not in off
         self.fork_epoch = str(args.get('graph_fork_epoch', os.environ.get('MMB_GRAPH_FORK_EPOCH', '0'))) not in off
         self.side = torch.cuda.Stream(device=device) if (self.fork or self.fork_epoch) else None
+        # Step-cache mode (args['_step_cache'], sweep.py): this stepper outlives the call and serves later grid points
+        # of the same structure.  Whatever differs between them must then live in device memory, not in the captured
+        # launches: the likelihood weights of losses.py:267-272 (and, for the e2e loop, of simplesif.py:786) become
+        # one-element tensors that ``rebind`` rewrites.  Same float32 values, same kernels, same rounding.
+        self.cache_mode = args.get('_step_cache') is not None
+        if self.cache_mode:
+            self.args = dict(args)
+            self.loss_w = torch.zeros(4, dtype=torch.float32, device=device)    # other_w, word_w, like_w, 1 - like_w
+            self.args['_loss_weights_dev'] = (self.loss_w[0:1], self.loss_w[1:2]) if 'word_loss_weight' in args else None
+            self._set_weights(args)
+
+    def _set_weights(self, args):
+        n_mod = len(self.gen_model.embed2out)
+        ww = float(args['word_loss_weight']) if 'word_loss_weight' in args else 1.
+        ow = (1. - ww) / n_mod if 'word_loss_weight' in args else 1.
+        lw = float(args.get('likelihood_weight', 1.))
+        self.loss_w.copy_(torch.tensor([ow, ww, lw, 1. - lw], dtype=torch.float64).to(torch.float32), non_blocking=True)
+
+    def rebind(self, args, embed_init):
+        """Serve another call with the captured graphs: new initial latents, new likelihood weights, optimizer
+        state back to zero (the generator / regressor parameters were re-initialised in place by the caller)."""
+        with torch.no_grad():
+            self.embeddings.copy_(torch.as_tensor(np.asarray(embed_init), dtype=torch.float32), non_blocking=True)
+            for st in self.optimizer.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+        self._set_weights(args)
+        self.status.zero_()
 
     def _gather(self, j):
         """``dataset[j]`` (reference utils.py:231-233 / 248-251) as one multi-tensor gather launch."""
@@ -503,19 +532,30 @@ def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epoc
     ``args['cuda_graph']`` (or MMB_CUDA_GRAPH=1) replays each step as one captured CUDA graph
     (``GraphedStep``); the default is the eager loop, launch for launch what the reference does.
     """
-    embeddings = torch.tensor(np.array(embed_arr, copy=True), device=device, dtype=torch.float32)
-    embeddings.requires_grad = True
-
-    grad_params = [embeddings]
-    if train and not args['freeze_weights']:
-        grad_params.extend(gen_model.parameters())
     graphed = _use_cuda_graph(args, gen_model, device)
-    if graphed and args['optimizer'] == 'adam':
-        optimizer = optim.Adam(grad_params, lr=lr, capturable=True)
+    train_heads = bool(train and not args['freeze_weights'])
+    cache = args.get('_step_cache') if graphed else None
+    cache_key = ('latents', train_heads, id(gen_model), id(dataloader.dataset), args['optimizer'], float(lr),
+                 str(args.get('cuda_graph')), 'word_loss_weight' in args)
+    if cache is not None and cache_key in cache:
+        # a captured step for exactly this structure (same generator object, dataset, optimizer, step size) exists:
+        # re-use its graphs on fresh latents (sweep.py; the nested validation passes of the e2e loop hit this too)
+        stepper, optimizer, embeddings = cache[cache_key]
+        stepper.rebind(args, embed_arr)
     else:
-        optimizer = _make_optimizer(args, grad_params, lr)
-    stepper = GraphedStep(args, gen_model, embeddings, dataloader.dataset, optimizer, word_prob_fn,
-                          device) if graphed else None
+        embeddings = torch.tensor(np.array(embed_arr, copy=True), device=device, dtype=torch.float32)
+        embeddings.requires_grad = True
+        grad_params = [embeddings]
+        if train_heads:
+            grad_params.extend(gen_model.parameters())
+        if graphed and args['optimizer'] == 'adam':
+            optimizer = optim.Adam(grad_params, lr=lr, capturable=True)
+        else:
+            optimizer = _make_optimizer(args, grad_params, lr)
+        stepper = GraphedStep(args, gen_model, embeddings, dataloader.dataset, optimizer, word_prob_fn,
+                              device) if graphed else None
+        if cache is not None:
+            cache[cache_key] = (stepper, optimizer, embeddings)
     moments = None if graphed else _dataset_moments(args, dataloader.dataset)
 
     valid_niter = 10
@@ -571,6 +611,8 @@ def optimize_latents(args, train: bool, gen_model, embed_arr, dataloader, n_epoc
         print("(Final) Validation loss:", valid_losses[0][-1])
         all_valid_losses.append(valid_losses[0][-1])
 
+    if cache is not None:
+        return embeddings.detach().clone(), (losses.floats(), all_valid_losses)    # the static tensor serves the next call
     embeddings.requires_grad = False
     return embeddings, (losses.floats(), all_valid_losses)
 
@@ -610,16 +652,13 @@ def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, 
     (reference 796-800) -- besides the number it reports, that pass draws from torch's global
     generator (one DataLoader base seed per epoch), so it is part of reproducing the reference's
     batch order.  Returns ``(train_embed, (train_losses, all_valid_losses))``."""
-    train_embed = torch.tensor(np.array(train_embedding, copy=True), device=device, dtype=torch.float32)
-    train_embed.requires_grad = True
-    grad_params = [train_embed] + list(gen_model.parameters()) + list(senti_model.parameters())
     graphed = _use_cuda_graph(args, gen_model, device)
-    if graphed and args['optimizer'] == 'adam':
-        optimizer = optim.Adam(grad_params, lr=args['lr'], capturable=True)
-    else:
-        optimizer = _make_optimizer(args, grad_params, args['lr'])
+    cache = args.get('_step_cache') if graphed else None
+    cache_key = ('e2e', id(gen_model), id(senti_model), id(senti_train_data), id(senti_mask), id(dataloader.dataset),
+                 args['optimizer'], float(args['lr']), str(args.get('cuda_graph')), 'word_loss_weight' in args)
     loss_function = nn.L1Loss(reduction='none')
     like_w = args['likelihood_weight']
+    holder = {}
 
     def mixed_loss(j, e, log_prob):
         """reference simplesif.py:776-786: L1 sentiment term, masked, mixed with the likelihood."""
@@ -628,10 +667,27 @@ def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, 
         if senti_loss.dim() > 1:
             senti_loss = senti_loss.mean(-1)
         senti_loss = senti_loss * senti_mask[j].reshape(senti_loss.shape)
+        st = holder.get('stepper')
+        if st is not None and st.cache_mode:                      # weights from device memory (GraphedStep.rebind)
+            return st.loss_w[2] * log_prob + st.loss_w[3] * senti_loss
         return like_w * log_prob + (1. - like_w) * senti_loss
 
-    stepper = GraphedStep(args, gen_model, train_embed, dataloader.dataset, optimizer, word_prob_fn, device,
-                          extra_loss=mixed_loss, extra_modules=[senti_model]) if graphed else None
+    if cache is not None and cache_key in cache:
+        stepper, optimizer, train_embed = cache[cache_key]
+        stepper.rebind(args, train_embedding)
+    else:
+        train_embed = torch.tensor(np.array(train_embedding, copy=True), device=device, dtype=torch.float32)
+        train_embed.requires_grad = True
+        grad_params = [train_embed] + list(gen_model.parameters()) + list(senti_model.parameters())
+        if graphed and args['optimizer'] == 'adam':
+            optimizer = optim.Adam(grad_params, lr=args['lr'], capturable=True)
+        else:
+            optimizer = _make_optimizer(args, grad_params, args['lr'])
+        stepper = GraphedStep(args, gen_model, train_embed, dataloader.dataset, optimizer, word_prob_fn, device,
+                              extra_loss=mixed_loss, extra_modules=[senti_model]) if graphed else None
+        holder['stepper'] = stepper
+        if cache is not None:
+            cache[cache_key] = (stepper, optimizer, train_embed)
     moments = None if graphed else _dataset_moments(args, dataloader.dataset)
     train_losses, all_valid_losses = _EpochLosses(), []
     start_time = time.time()
@@ -676,6 +732,8 @@ def train_end_to_end(args, gen_model, senti_model, train_embedding, dataloader, 
                 if verbose:
                     print("Validation loss:", valid_losses[-1])
                 all_valid_losses.append(valid_losses[-1])
+    if cache is not None:
+        return train_embed.detach().clone(), (train_losses.floats(), all_valid_losses)
     train_embed.requires_grad = False
     return train_embed, (train_losses.floats(), all_valid_losses)
 

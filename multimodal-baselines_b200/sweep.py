@@ -107,6 +107,22 @@ class Prepared(object):
         self.raw, self.masks, self.We, self.weights = raw, masks, We, weights
         self.by_pos = {}
         self.embeddings = None
+        # Captured steps and the modules they were captured on, kept across grid points (``graph_cache``): grid
+        # points of the same structure (pos_embed_dim, norm, optimizer, step size, regressor width) re-use the graphs;
+        # their parameters are re-initialised IN PLACE from a freshly constructed module (same draws from the
+        # generator, same values), their likelihood weights are device scalars (simplesif.GraphedStep.rebind).
+        self.step_cache = {}
+        self.modules = {}
+        self.senti_train_data = None
+        self.senti_mask = None
+
+    def persistent_module(self, key, fresh):
+        """The module kept for ``key``, holding ``fresh``'s parameters and buffers (copied in place)."""
+        if key not in self.modules:
+            self.modules[key] = fresh.to(self.device)
+        else:
+            self.modules[key].load_state_dict(fresh.state_dict())
+        return self.modules[key]
 
     def for_pos(self, pos_embed_dim):
         import copy
@@ -129,7 +145,7 @@ class Prepared(object):
         return self.by_pos[pos_embed_dim]
 
 
-def run_config(cfg, prep, epochs_scale=1.0, cuda_graph=True, verbose=False, defer_regressor=False):
+def run_config(cfg, prep, epochs_scale=1.0, cuda_graph=True, verbose=False, defer_regressor=False, graph_cache=False):
     """One grid point, reference simplesif.py:625-914 (e2e branch).  Returns the test metrics of
     the downstream regressor and the final losses.  ``defer_regressor``: stop after the latent phases and
     return the regressor problem as a ``sentiment_batched.RegressorJob`` under ``'job'`` (with the random
@@ -147,9 +163,21 @@ def run_config(cfg, prep, epochs_scale=1.0, cuda_graph=True, verbose=False, defe
     torch.manual_seed(1000 + cfg['config_num'])
     word_fn = simplesif.make_word_log_prob_fn(args, w_t, we_t)
     gen_model = AudioVisualGeneratorMultimodal(d, A, Vd, norm=args['norm'], frozen_weights=args['freeze_weights'],
-                                               unimodal=False).to(device)
-    senti_model = SentimentModel(d, args['sentiment_hidden_size'], 1).to(device)
-    senti_mask = torch.ones(len(prep.labels[0]), device=device)
+                                               unimodal=False)
+    senti_model = SentimentModel(d, args['sentiment_hidden_size'], 1)
+    if graph_cache and cuda_graph:
+        # ``graph_cache``: same values as a fresh module, but in the persistent module the cached graphs read
+        args['_step_cache'] = prep.step_cache
+        gen_model = prep.persistent_module(('gen', cfg['pos_embed_dim'], args['norm'], args['freeze_weights']), gen_model)
+        senti_model = prep.persistent_module(('senti', args['sentiment_hidden_size']), senti_model)
+        if prep.senti_train_data is None:
+            prep.senti_train_data = SentimentData(prep.labels[0], device)
+            prep.senti_mask = torch.ones(len(prep.labels[0]), device=device)
+        senti_train_data, senti_mask = prep.senti_train_data, prep.senti_mask
+    else:
+        gen_model, senti_model = gen_model.to(device), senti_model.to(device)
+        senti_train_data = SentimentData(prep.labels[0], device)
+        senti_mask = torch.ones(len(prep.labels[0]), device=device)
     # The reference's helpers print progress and, on a non-finite log-probability, print the
     # modality names and sys.exit() (losses.py:258-264) -- in the reference one config is one
     # process; here that exit marks the config as diverged and the sweep goes on.
@@ -168,7 +196,7 @@ def run_config(cfg, prep, epochs_scale=1.0, cuda_graph=True, verbose=False, defe
         t_last[0] = now
     try:
         train_embed, (train_losses, _) = simplesif.train_end_to_end(
-            args, gen_model, senti_model, prep.embeddings[0], loaders[0], SentimentData(prep.labels[0], device),
+            args, gen_model, senti_model, prep.embeddings[0], loaders[0], senti_train_data,
             senti_mask, word_fn, device, verbose=False, validation_data=(prep.embeddings[1], loaders[1]))
         lap('train_e2e_incl_nested_validation')
         valid_embed, _ = simplesif.optimize_latents(args, False, gen_model, prep.embeddings[1], loaders[1],
@@ -208,6 +236,9 @@ def main(argv=None):
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--only', type=int, nargs='*', default=None, help='run just these config numbers')
     ap.add_argument('--out', default='')
+    ap.add_argument('--no-graph-cache', action='store_true',
+                    help='capture every grid point\'s graphs anew (default: grid points of the same structure '
+                         're-use the captured steps; results are bit-identical either way)')
     ap.add_argument('--regressor-batch', type=int, default=8,
                     help='train the downstream regressors of this many grid points as one batched model '
                          '(SURVEY 8f N4; 1 = the sequential module per grid point)')
@@ -249,8 +280,8 @@ def main(argv=None):
     if a.regressor_batch > 1:
         import sentiment_batched
         for o in range(0, len(mine), a.regressor_batch):
-            part = [run_config(cfg, prep, a.epochs_scale, not a.no_graph, defer_regressor=True)
-                    for cfg in mine[o:o + a.regressor_batch]]
+            part = [run_config(cfg, prep, a.epochs_scale, not a.no_graph, defer_regressor=True,
+                               graph_cache=not a.no_graph_cache) for cfg in mine[o:o + a.regressor_batch]]
             jobs = [r['job'] for r in part if 'job' in r]
             t_reg = time.perf_counter()
             buf, old_stdout = open(os.devnull, 'w'), sys.stdout
@@ -269,7 +300,7 @@ def main(argv=None):
                     r['phase_s']['sentiment_regressor_batched_share'] = round(t_reg, 3)
             out.extend(part)
     else:
-        out = [run_config(cfg, prep, a.epochs_scale, not a.no_graph) for cfg in mine]
+        out = [run_config(cfg, prep, a.epochs_scale, not a.no_graph, graph_cache=not a.no_graph_cache) for cfg in mine]
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if world > 1:
@@ -290,7 +321,7 @@ def main(argv=None):
                           'processes_per_gpu': max(1, world // max(n_dev, 1)), 'seconds': dt, 'value': len(out) / dt,
                           'value_per_gpu': len(out) / dt / max(1, min(world, n_dev)),
                           'epochs_scale': a.epochs_scale, 'cuda_graph': not a.no_graph,
-                          'regressor_batch': a.regressor_batch,
+                          'regressor_batch': a.regressor_batch, 'graph_cache': not a.no_graph_cache,
                           'diverged': [r['config_num'] for r in out if r.get('diverged')],
                           'best_test_MAE': (min(maes) if maes else None)}), flush=True)
 

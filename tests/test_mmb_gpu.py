@@ -562,3 +562,33 @@ def test_data_parallel_loop_single_rank_matches_reference_loop(mods, golden_dir,
     close(np.array(losses_), g[tag + '_losses'], LOOP_RTOL, 'losses')
     close(emb.cpu(), g[tag + '_emb'], LOOP_RTOL, 'latents')
     close(model.embed2out['audio']['mu'].weight.detach().cpu(), g[tag + '_Wmu_audio'], LOOP_RTOL, 'W')
+
+
+def test_sweep_graph_cache_is_bit_identical(mods, capsys):
+    """sweep.py re-uses captured steps across grid points of the same structure (persistent generator / regressor
+    modules re-initialised in place, likelihood weights as device scalars, optimizer state reset).  A sequence of grid
+    points that share graphs -- differing in likelihood_weight (bit 3 of the index), word_loss_weight (bit 4), regressor
+    width (bit 8: new e2e graph, shared inference graphs) and lr (bit 7: new graphs) -- must give bit-for-bit the
+    losses and metrics of runs that capture everything anew; a BatchNorm + SGD point that diverges must still diverge."""
+    torch = mods[0]
+    import copy
+    import sweep
+    grid = sweep.make_grid()
+    dev = torch.device('cuda')
+    We, weights, splits = sweep.synthetic_mosi(seed=4, sizes=(200, 60, 90), V=400)
+    scale = 0.04
+    seq = [1, 9, 17, 257, 129, 1, 3, 11, 2, 10]
+    cached = sweep.Prepared(We, weights, copy.deepcopy(splits), dev)
+    got = [sweep.run_config(grid[k], cached, epochs_scale=scale, graph_cache=True) for k in seq]
+    n_keys = len(cached.step_cache)
+    fresh = sweep.Prepared(We, weights, copy.deepcopy(splits), dev)
+    want = [sweep.run_config(grid[k], fresh, epochs_scale=scale, graph_cache=False) for k in seq]
+    capsys.readouterr()
+    assert 0 < n_keys < 3 * len(set(seq))            # graphs were shared (a fresh capture per point would be 3 per point)
+    for k, g, w in zip(seq, got, want):
+        assert g.get('diverged') == w.get('diverged'), k
+        if w.get('diverged'):
+            continue
+        assert g['train_loss'] == w['train_loss'] and g['test_loss'] == w['test_loss'], (k, g['train_loss'], w['train_loss'])
+        for m in ('mae', 'corr', 'accuracy', 'mult_acc', 'f_score'):
+            assert g['results'][m] == w['results'][m], (k, m)
