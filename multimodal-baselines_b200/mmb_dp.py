@@ -32,7 +32,6 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-import mmb_ops
 
 
 class DataParallel(object):
