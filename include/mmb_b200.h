@@ -111,6 +111,20 @@ MMB_API int mmb_sif_embed_ws(const float* table, int64_t V, int d, const float* 
                              int64_t N, int64_t L, float* emb, int* status, void* ws, size_t ws_bytes,
                              mmb_stream_t stream);
 
+/* get_weighted_average + the Gram that compute_pc needs (sif_functions.py:28-67) of one block in one call.
+ * With option "overlap_sms" = S > 0 (mmb_set_option; default 0) the Gram is taken BESIDE the embed: the block
+ * is cut into "overlap_chunks" chunks and chunk c's tcgen05 Gram runs on S SMs from an internal
+ * higher-priority stream while chunk c + 1 is embedded on the others.  Measured slower than one stage after
+ * the other on a B200 (33.6 vs 31.4 ms per 10 M utterances, tools/overlap_probe.py), hence off: the call is
+ * then mmb_sif_embed_ws followed by mmb_gram.  emb (N, d) and G (d, d) = emb^T emb are complete when the
+ * work enqueued on `stream` by this call completes; chunk Grams are added in chunk order (deterministic,
+ * within 2e-6 relative of mmb_gram's grouping).
+ * ws: mmb_sif_embed_gram_workspace_bytes(V, d, N, L, gram_mode) bytes, 256-byte aligned.               */
+MMB_API size_t mmb_sif_embed_gram_workspace_bytes(int64_t V, int d, int64_t N, int64_t L, int gram_mode);
+MMB_API int mmb_sif_embed_gram(const float* table, int64_t V, int d, const float* vocab_w, const int64_t* x,
+                               int64_t N, int64_t L, float* emb, int* status, float* G, void* ws,
+                               size_t ws_bytes, int gram_mode, mmb_stream_t stream);
+
 /* Ragged (CSR) ids, SURVEY.md 8f N3 -- the same result as mmb_sif_embed on the right-padded (N, L_pad)
  * matrix the reference builds (utils.py:77-80; sif_functions.py:28-56), without walking the padding:
  * utterance i is tokens[offsets[i] .. offsets[i+1]) (int64, offsets has N + 1 entries) and is understood

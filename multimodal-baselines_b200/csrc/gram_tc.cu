@@ -418,9 +418,10 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static int plan(int64_t N) {
+static int plan(int64_t N, int max_cta = 0) {
   const int64_t kblocks = (N + kBK - 1) / kBK;
-  const int sms = sm_count();
+  int sms = sm_count();
+  if (max_cta > 0 && max_cta < sms) sms = max_cta;   // leave the other SMs to a concurrent kernel (api.cu)
   return (int)(kblocks < sms ? (kblocks > 0 ? kblocks : 1) : sms);
 }
 
@@ -443,12 +444,13 @@ size_t gram_tc_workspace_bytes(int64_t N, int d) {
   return (size_t)tc::plan(N) * tc::kPartialStride * sizeof(float);
 }
 
-static int gram_tc_main(const float* X, int64_t N, int d, void* ws, size_t ws_bytes, cudaStream_t st, int* n_cta_out) {
+static int gram_tc_main(const float* X, int64_t N, int d, void* ws, size_t ws_bytes, cudaStream_t st, int* n_cta_out,
+                        int max_cta = 0) {
   using namespace tc;
   MMB_REQUIRE(d == kD, "tcgen05 Gram is specialised for d == 300");
   MMB_REQUIRE(N < ((int64_t)1 << 31) - 64, "N too large for 32-bit TMA coordinates");
-  const int n_cta = plan(N);
-  MMB_REQUIRE(ws_bytes >= gram_tc_workspace_bytes(N, d), "workspace too small");
+  const int n_cta = plan(N, max_cta);
+  MMB_REQUIRE(ws_bytes >= (size_t)n_cta * kPartialStride * sizeof(float), "workspace too small");
   EncodeTiledFn enc = encode_fn();
   if (!enc) {
     set_error("gram_tc: cuTensorMapEncodeTiled is not available");
@@ -489,10 +491,11 @@ static int gram_tc_main(const float* X, int64_t N, int d, void* ws, size_t ws_by
   return MMB_OK;
 }
 
-int gram_tc(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_bytes, cudaStream_t st) {
+// max_cta > 0: at most that many CTAs (= SMs; one persistent CTA per SM), for a Gram that runs beside another kernel.
+int gram_tc(const float* X, int64_t N, int d, float* G, void* ws, size_t ws_bytes, cudaStream_t st, int max_cta) {
   using namespace tc;
   int n_cta = 0;
-  const int rc = gram_tc_main(X, N, d, ws, ws_bytes, st, &n_cta);
+  const int rc = gram_tc_main(X, N, d, ws, ws_bytes, st, &n_cta, max_cta);
   if (rc) return rc;
   gram_tc_reduce_kernel<<<(kD * kD + 255) / 256, 256, 0, st>>>((const float*)ws, n_cta, G);
   MMB_LAUNCH_CHECK("gram_tc_reduce");

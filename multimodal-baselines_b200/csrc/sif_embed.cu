@@ -956,15 +956,18 @@ int sif_prescale(const float* table, int64_t V, int d, const float* vocab_w, voi
 }
 
 // The embed pass on a pre-scaled table (ws from sif_prescale) with the general kernel standing by.
+// grid_mult: CTAs per SM of the grid-stride launch (4 are resident).  8 for a kernel that owns the GPU; the
+// Gram-overlap pipeline (api.cu) asks for more, smaller CTAs so that SMs freed by the Gram are refilled.
 int sif_embed_prescaled(const float* table, int64_t V, int d, const float* vocab_w, const void* ws, const int64_t* x,
-                        int64_t N, int64_t L, float* emb, int* status, cudaStream_t st) {
+                        int64_t N, int64_t L, float* emb, int* status, cudaStream_t st, int grid_mult) {
   if (N == 0) return MMB_OK;
   const int d4 = d / 4;
   const int* flags = (const int*)ws;
   const float4* tp4 = (const float4*)((const char*)ws + 256);
   const int sms = sm_count();
   const int64_t blocks = ceil_div(N, kEmbedWarps);
-  const int grid = (int)(blocks < (int64_t)sms * 8 ? blocks : (int64_t)sms * 8);
+  if (grid_mult < 1) grid_mult = 8;
+  const int grid = (int)(blocks < (int64_t)sms * grid_mult ? blocks : (int64_t)sms * grid_mult);
   if (sif_embed_hot_eligible(V, d, N, L)) {
     // very large batches: the most frequent rows on the tensor cores (sif_embed_hot.cu); the general kernel
     // still stands by for the zero-weight case
@@ -1035,5 +1038,5 @@ extern "C" int mmb_sif_embed_ws(const float* table, int64_t V, int d, const floa
               "table / emb / ws must be 16-byte aligned");
   int rc = sif_prescale(table, V, d, vocab_w, ws, as_stream(stream));
   if (rc) return rc;
-  return sif_embed_prescaled(table, V, d, vocab_w, ws, x, N, L, emb, status, as_stream(stream));
+  return sif_embed_prescaled(table, V, d, vocab_w, ws, x, N, L, emb, status, as_stream(stream), 8);
 }
