@@ -58,6 +58,31 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], "
+      "[%4], %5;"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float ld_hint(const float* p, uint64_t policy) {
+  float v;
+  asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_hint(float* p, float v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -91,6 +116,31 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// The same MMA with a hint for the A-operand collector buffer (SASS UTCHMMA .A_KEEP / .A_REUSE): consecutive MMAs
+// that share their A tile (same descriptor, M and K) read it from shared memory once.
+enum : int { kCollectDiscard = 0, kCollectFill = 1, kCollectUse = 2, kCollectLastUse = 3 };
+template <int MODE>
+__device__ __forceinline__ void umma_tf32_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  if constexpr (MODE == kCollectFill) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else if constexpr (MODE == kCollectUse) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::use [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else if constexpr (MODE == kCollectLastUse) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+  }
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -113,6 +163,9 @@ struct Params {
   int passes;         // 3 = 3xTF32, 1 = plain TF32 (debug)
   int seg;            // K blocks accumulated in TMEM between two flushes to the FP32 partial
   int prefetch;       // K blocks of L2 prefetch distance (0 = off)
+  int opt;            // bit 0: flush skips warp-chunks below the diagonal; bit 1: L2 eviction hints (X evict_first,
+                      // partial evict_last); bit 2: block C pairs packed into full warps
+  int collect;        // 1: A-sharing MMA order with collector reuse hints; 2: that order without the hints; 0: pass order
   uint32_t lbo, sbo;  // descriptor strides in bytes
   float* partial;
 };
@@ -164,6 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      const uint64_t pol_stream = l2_policy_evict_first();   // X is read once
       for (int64_t i = 0; i < nkb; ++i) {
         const int s = (int)(i % kStages);
         const uint32_t ph = (uint32_t)((i / kStages) & 1);
@@ -177,8 +231,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_expect_tx(bar_full + 8 * s, (uint32_t)kHiBytes);
         const uint32_t dst = smem_base + s * kStageBytes;
         const int row = (int)((kb0 + i) * kBK);
-        for (int b = 0; b < kBoxes; ++b)
-          tma_load_2d(dst + b * kBoxBytes, &tmap, b * 32, row, bar_full + 8 * s);
+        if (prm.opt & 2) {
+          for (int b = 0; b < kBoxes; ++b)
+            tma_load_2d_hint(dst + b * kBoxBytes, &tmap, b * 32, row, bar_full + 8 * s, pol_stream);
+        } else {
+          for (int b = 0; b < kBoxes; ++b)
+            tma_load_2d(dst + b * kBoxBytes, &tmap, b * 32, row, bar_full + 8 * s);
+        }
       }
     }
   } else if (warp == 1) {
@@ -206,6 +265,38 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int ks = 0; ks < kBK / 8; ++ks) {
             const uint32_t koff = ks * 1024;  // 8 K rows = two 4-row swizzle atoms of 512 B
+            if (prm.passes == 3 && prm.collect != 0) {
+              // The nine MMAs of a K step ordered by A tile, so that each of the four A tiles (hi / lo x rows
+              // 0..127 / 128..255) is fetched from shared memory once instead of 9 times in total: the A
+              // collector keeps it across the MMAs that share it.  Sums are the same terms in another order.
+              const uint32_t z = (first && ks == 0) ? 0u : 1u;
+              const uint64_t h0 = desc_at(dbase, hi + koff), h4 = desc_at(dbase, hi + koff + 4 * blk),
+                             h8 = desc_at(dbase, hi + koff + 8 * blk);
+              const uint64_t l0 = desc_at(dbase, lo + koff), l4 = desc_at(dbase, lo + koff + 4 * blk),
+                             l8 = desc_at(dbase, lo + koff + 8 * blk);
+              if (prm.collect == 1) {
+                umma_tf32_c<kCollectFill>(tmem + 0, h0, l0, idesc256, z);        // hi[0:128]   x lo[0:256]
+                umma_tf32_c<kCollectUse>(tmem + 256, h0, l8, idesc48, z);        //             x lo[256:304]
+                umma_tf32_c<kCollectUse>(tmem + 0, h0, h0, idesc256, 1u);        //             x hi[0:256]
+                umma_tf32_c<kCollectLastUse>(tmem + 256, h0, h8, idesc48, 1u);   //             x hi[256:304]
+                umma_tf32_c<kCollectFill>(tmem + 304, h4, l4, idesc176, z);      // hi[128:256] x lo[128:304]
+                umma_tf32_c<kCollectLastUse>(tmem + 304, h4, h4, idesc176, 1u);  //             x hi[128:304]
+                umma_tf32_c<kCollectFill>(tmem + 0, l0, h0, idesc256, 1u);       // lo[0:128]   x hi[0:256]
+                umma_tf32_c<kCollectLastUse>(tmem + 256, l0, h8, idesc48, 1u);   //             x hi[256:304]
+                umma_tf32_c<kCollectDiscard>(tmem + 304, l4, h4, idesc176, 1u);  // lo[128:256] x hi[128:304]
+              } else {
+                umma_tf32(tmem + 0, h0, l0, idesc256, z);
+                umma_tf32(tmem + 256, h0, l8, idesc48, z);
+                umma_tf32(tmem + 0, h0, h0, idesc256, 1u);
+                umma_tf32(tmem + 256, h0, h8, idesc48, 1u);
+                umma_tf32(tmem + 304, h4, l4, idesc176, z);
+                umma_tf32(tmem + 304, h4, h4, idesc176, 1u);
+                umma_tf32(tmem + 0, l0, h0, idesc256, 1u);
+                umma_tf32(tmem + 256, l0, h8, idesc48, 1u);
+                umma_tf32(tmem + 304, l4, h4, idesc176, 1u);
+              }
+              continue;
+            }
             for (int p = 0; p < prm.passes; ++p) {
               // small terms first (lo*hi, hi*lo), then hi*hi; the MMA ignores the low 13
               // mantissa bits of its FP32 operands, so "hi" is the raw TMA tile.
@@ -233,6 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int row = q * 32 + lane;
     float* part = prm.partial + (size_t)blockIdx.x * kPartialStride;
     float* outT = part + row;   // column-major tiles A|B: element (row, c) at part[c * 128 + row]
+    const uint64_t pol_keep = l2_policy_evict_last();   // the partial is re-read at every flush: keep it in L2
     int64_t i = 0;
     for (int64_t sg = 0; sg < nseg; ++sg) {
       int64_t iend = i + prm.seg;
@@ -265,13 +357,31 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_wait(bar_done, (uint32_t)(sg & 1));
       tc_fence_after();
       for (int c = 0; c < kColsAB; c += 32) {
+        // warp-chunks entirely below the diagonal are never read by the reduce kernel: tile A (rows 32 q ..,
+        // columns c ..) when c + 32 <= 32 q; tile B (rows 128 + 32 q .., columns 128 + c - 304 ..) likewise
+        if ((prm.opt & 1) && (c + 32 <= 32 * q || (c >= 320 && c - 304 + 32 <= 32 * q))) continue;
         float* o = outT + (size_t)c * 128;
         float old[32];
+        uint32_t r[32];
+        if (prm.opt & 2) {
+          if (sg > 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) old[j] = ld_hint(o + (size_t)j * 128, pol_keep);
+          }
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c, r);
+          if (sg == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) st_hint(o + (size_t)j * 128, __uint_as_float(r[j]), pol_keep);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) st_hint(o + (size_t)j * 128, old[j] + __uint_as_float(r[j]), pol_keep);
+          }
+          continue;
+        }
         if (sg > 0) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) old[j] = o[(size_t)j * 128];
         }
-        uint32_t r[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c, r);
         if (sg == 0) {
 #pragma unroll
@@ -291,7 +401,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ===== corner warps: block C (rows/cols 256..299, does not fit in TMEM) in exact FP32 from the
     // raw tile; 11 x 11 grid of 4x4 blocks, upper triangle (66 pairs), dealt round-robin =====
     float* part = prm.partial + (size_t)blockIdx.x * kPartialStride;
-    const int pidx = lane * 4 + (warp - 6);
+    // pair index: dealt over the four warps, or (opt bit 2) packed into two full warps + 2 lanes -- the cost of a
+    // warp-wide LDS.128 here is its 2-3 shared-memory wavefronts whatever the number of active lanes
+    const int pidx = (prm.opt & 4) ? (warp - 6) * 32 + lane : lane * 4 + (warp - 6);
     int ti = 0, tj = 0;
     const bool has_c = pidx < 66;
     if (has_c) {
@@ -484,6 +596,10 @@ static int gram_tc_main(const float* X, int64_t N, int d, void* ws, size_t ws_by
   if (const char* e = getenv("MMB_TC_PASSES")) prm.passes = atoi(e) == 1 ? 1 : 3;
   if (const char* e = getenv("MMB_TC_SEG")) prm.seg = atoi(e) > 0 ? atoi(e) : kSegDefault;
   if (const char* e = getenv("MMB_TC_PREFETCH")) prm.prefetch = atoi(e);
+  prm.opt = 7;          // measured (tools/gram_probe.py, profiles/r02_gram_probe.jsonl): each of the three helps
+  if (const char* e = getenv("MMB_TC_OPT")) prm.opt = atoi(e);
+  prm.collect = 1;      // A-sharing MMA order + collector hints: -4 ... -7 % (same probe)
+  if (const char* e = getenv("MMB_TC_COLLECT")) prm.collect = atoi(e);
   prm.partial = (float*)ws;
   gram_tc_kernel<<<n_cta, kThreads, kSmemBytes, st>>>(tmap, prm);
   MMB_LAUNCH_CHECK("gram_tc");

@@ -22,6 +22,7 @@ import numpy as np
 import torch
 from torch.utils.data import DataLoader
 
+import graph_capture
 from sentiment_model import SentimentModel, _score
 
 
@@ -146,7 +147,7 @@ def train_batched(jobs, device, valid_niter=10, use_graph=True):
             for p, s_ in zip(net.params, saved):
                 p.copy_(s_)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with graph_capture.capture(graph):
             static_total = epoch_body()
 
     def eval_pass(split, order):

@@ -21,6 +21,7 @@ import torch.nn.functional as F
 import torch.optim as optim
 from torch.utils.data import DataLoader, Dataset
 
+import graph_capture
 from losses import full_loss, iemocap_loss, pom_loss
 
 
@@ -149,7 +150,7 @@ class _GraphedSentimentStep(object):
                     p.copy_(s)
             graph = torch.cuda.CUDAGraph()
             self.optimizer.zero_grad(set_to_none=True)
-            with torch.cuda.graph(graph):
+            with graph_capture.capture(graph):
                 static_loss = self._step(static_j)
             self.graphs[n] = (graph, static_j, static_loss)
         graph, static_j, static_loss = self.graphs[n]
@@ -178,7 +179,7 @@ class _GraphedSentimentStep(object):
                     p.copy_(s_)
             graph = torch.cuda.CUDAGraph()
             self.optimizer.zero_grad(set_to_none=True)
-            with torch.cuda.graph(graph):
+            with graph_capture.capture(graph):
                 total = torch.zeros((), device=dev)
                 off = 0
                 for n in key:

@@ -28,6 +28,7 @@ from torch.utils.data import DataLoader
 
 from losses import CatSegments, MomentStats, TokenIds, get_log_prob_matrix, get_word_log_prob_angular, get_word_log_prob_dot_prod  # noqa: F401
 from losses import get_word_log_prob_angular2
+import graph_capture
 import mmb_ops
 from models import AudioVisualGeneratorConcat, AudioVisualGenerator, AudioVisualGeneratorMultimodal  # noqa: F401
 from sentiment_model import SentimentData, SentimentModel, train_sentiment_for_latents
@@ -373,7 +374,7 @@ class GraphedStep(object):
                             st[k].copy_(v)
         graph = torch.cuda.CUDAGraph()
         self.optimizer.zero_grad(set_to_none=True)
-        with torch.cuda.graph(graph):
+        with graph_capture.capture(graph):
             static_loss = self._step(static_j)
         # the capture itself does not execute; state is untouched
         self._keepalive.extend(self.mmb_ops.cached_inv_norms())   # buffers whose addresses the graph holds
@@ -428,7 +429,7 @@ class GraphedStep(object):
                             st[k].copy_(v)
         graph = torch.cuda.CUDAGraph()
         self.optimizer.zero_grad(set_to_none=True)
-        with torch.cuda.graph(graph):
+        with graph_capture.capture(graph):
             total = torch.zeros((), device=self.device)
             off = 0
             for n in sizes:
