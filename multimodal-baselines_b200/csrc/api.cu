@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -220,6 +221,8 @@ struct SideStream {
 SideStream g_side[64];
 
 int side_stream(cudaStream_t* out) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
   int dev = 0;
   MMB_CUDA(cudaGetDevice(&dev));
   MMB_REQUIRE(dev >= 0 && dev < 64, "device ordinal out of range");
