@@ -17,7 +17,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
     # modes: collect[:seg[:passes[:opt]]] , ...   (the committed r02_gram_probe.jsonl also has 'dbg' rows from a build
     # with ablation switches: 1 = no block C, 2 = no split, 4 = no MMAs -- timing only, since removed)
-    modes = [tuple(int(x) for x in v.split(':')) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else [(0, 64, 3, 0), (1, 64, 3, 7), (0, 64, 3, 0), (1, 64, 3, 7)]
+    modes = [tuple(int(x) for x in v.split(':')) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else [(0, 64, 3, 0), (1, 64, 3, 15), (0, 64, 3, 0), (1, 64, 3, 15)]
     dev = torch.device('cuda')
     g = torch.Generator(device=dev).manual_seed(5)
     d = 300
@@ -33,7 +33,7 @@ def main():
         os.environ['MMB_TC_COLLECT'] = str(mode[0])
         os.environ['MMB_TC_SEG'] = str(mode[1] if len(mode) > 1 else 64)
         os.environ['MMB_TC_PASSES'] = str(mode[2] if len(mode) > 2 else 3)
-        os.environ['MMB_TC_OPT'] = str(mode[3] if len(mode) > 3 else 7)
+        os.environ['MMB_TC_OPT'] = str(mode[3] if len(mode) > 3 else 15)
         ms = []
         for it in range(8):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
