@@ -178,7 +178,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     fn, kind, how = reference_fn()
-    sample = int(os.environ.get('MMB_REF_SAMPLE', 20_000))     # same size as the GPU arm's cpu_baseline leg
+    sample = int(os.environ.get('MMB_REF_SAMPLE', 20_000))     # ~1 s per step: 23 steps (driver default) ~ 25 s in all
     rng = np.random.default_rng(0)
     p = zipf_pmf(VOCAB)
     table = (0.4 * rng.standard_normal((VOCAB, DIM), dtype=np.float32)
@@ -715,7 +715,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sample = int(os.environ.get('MMB_CPU_SAMPLE', 20_000))
+        sample = int(os.environ.get('MMB_CPU_SAMPLE', 200_000))       # ~10 s of the reference's Python loops
         sample = min(sample, n_local)
         rate, secs, kind, how = cpu_port_rate(table.cpu().numpy(), vocab_w.double().cpu().numpy(),
                                               ids[:sample].cpu().numpy())
