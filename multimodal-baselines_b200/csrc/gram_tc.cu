@@ -19,7 +19,11 @@
 //   MMA      : one elected thread issues tcgen05.mma (M = 128) for the upper-triangular blocks
 //                 tile A  rows   0..127 x cols   0..303   (N = 256 + 48)   TMEM cols   0..303
 //                 tile B  rows 128..255 x cols 128..303   (N = 176)        TMEM cols 304..479
-//              with three passes (lo*hi, hi*lo, hi*hi) per 8-row K step: 18 MMAs per stage.
+//              with three products (hi*lo, hi*hi, lo*hi) per 8-row K step: 18 MMAs per stage, issued BY A TILE
+//              (hi rows 0..127 x {lo, hi}, hi rows 128..255 x {lo, hi}, lo rows 0..127 x hi, lo rows 128..255 x
+//              hi) with .collector::a::fill/use/lastuse, so an A tile is fetched from shared memory once per
+//              K step instead of once per MMA; tile A's 304 columns go as N = 160 + 144.  (Shared-memory
+//              bandwidth -- operand fetch + the workers below -- is what bounds this kernel.)
 //   block C  : the remaining 44x44 block (rows/cols 256..299) does not fit in the 512 TMEM
 //              columns next to A and B (it would need 48 more), so the worker warps compute
 //              it on the CUDA cores in exact FP32 from the raw tile, 4x4 register blocks.
@@ -28,7 +32,10 @@
 //              over 6.7 k rows); every `seg` stages (default 64 = 1024 rows) the workers drain
 //              TMEM (tcgen05.ld) into the CTA's FP32 partial tile in global memory (L2-resident,
 //              column-major so that lane = row gives coalesced lines) with round-to-nearest
-//              adds, which bounds the bias at ~2e-5 relative.
+//              adds, which bounds the bias at ~2e-5 relative.  The partial is read and written with an
+//              L2 evict_last policy and X streams through the TMA with evict_first (otherwise the 190 MB
+//              of X between two flushes push the 38 MB of partials out to HBM); warp-chunks entirely
+//              below the diagonal are skipped (the reduce kernel never reads them).
 //   reduce   : a second kernel sums the per-CTA partials in CTA order (deterministic) and
 //              mirrors the upper triangle.
 #include <cuda.h>
@@ -166,7 +173,7 @@ struct Params {
   int opt;            // bit 0: flush skips warp-chunks below the diagonal; bit 1: L2 eviction hints (X evict_first,
                       // partial evict_last); bit 2: block C pairs packed into full warps; bit 3: tile A's 304
                       // columns as N = 160 + 144 instead of 256 + 48
-  int collect;        // 1: A-sharing MMA order with collector reuse hints; 2: that order without the hints; 0: pass order
+  int collect;        // 1: A-sharing MMA order with collector reuse hints; 0: pass order
   uint32_t lbo, sbo;  // descriptor strides in bytes
   float* partial;
 };
@@ -289,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 umma_tf32_c<kCollectFill>(tmem + 0, l0, h0, idesc160, 1u);
                 umma_tf32_c<kCollectLastUse>(tmem + 160, l0, h5, idesc144, 1u);
                 umma_tf32_c<kCollectDiscard>(tmem + 304, l4, h4, idesc176, 1u);
-              } else if (prm.collect == 1) {
+              } else {
                 umma_tf32_c<kCollectFill>(tmem + 0, h0, l0, idesc256, z);        // hi[0:128]   x lo[0:256]
                 umma_tf32_c<kCollectUse>(tmem + 256, h0, l8, idesc48, z);        //             x lo[256:304]
                 umma_tf32_c<kCollectUse>(tmem + 0, h0, h0, idesc256, 1u);        //             x hi[0:256]
@@ -299,16 +306,6 @@ __global__ void __launch_bounds__(kThreads, 1)
                 umma_tf32_c<kCollectFill>(tmem + 0, l0, h0, idesc256, 1u);       // lo[0:128]   x hi[0:256]
                 umma_tf32_c<kCollectLastUse>(tmem + 256, l0, h8, idesc48, 1u);   //             x hi[256:304]
                 umma_tf32_c<kCollectDiscard>(tmem + 304, l4, h4, idesc176, 1u);  // lo[128:256] x hi[128:304]
-              } else {
-                umma_tf32(tmem + 0, h0, l0, idesc256, z);
-                umma_tf32(tmem + 256, h0, l8, idesc48, z);
-                umma_tf32(tmem + 0, h0, h0, idesc256, 1u);
-                umma_tf32(tmem + 256, h0, h8, idesc48, 1u);
-                umma_tf32(tmem + 304, h4, l4, idesc176, z);
-                umma_tf32(tmem + 304, h4, h4, idesc176, 1u);
-                umma_tf32(tmem + 0, l0, h0, idesc256, 1u);
-                umma_tf32(tmem + 256, l0, h8, idesc48, 1u);
-                umma_tf32(tmem + 304, l4, h4, idesc176, 1u);
               }
               continue;
             }
