@@ -477,8 +477,11 @@ __global__ void __launch_bounds__(256)
   if (i < 128) p = partial + (size_t)j * 128 + i;
   else if (i < 256) p = partial + (size_t)(304 + (j - 128)) * 128 + (i - 128);
   else p = partial + 128 * kColsAB + (size_t)(i - 256) * kColsC + (j - 256);
+  // last use of the partials: read them with evict_first so that the lines the flush pinned (evict_last) stop
+  // occupying L2 once the Gram is done
+  const uint64_t pol = l2_policy_evict_first();
   float s = 0.f;
-  for (int c = 0; c < n_cta; ++c) s += p[(size_t)c * kPartialStride];
+  for (int c = 0; c < n_cta; ++c) s += ld_hint(p + (size_t)c * kPartialStride, pol);
   G[(size_t)i * kD + j] = s;
   G[(size_t)j * kD + i] = s;
 }
@@ -494,6 +497,7 @@ __global__ void __launch_bounds__(256)
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;      // cooperative launch: the whole grid is co-resident
   float* mine = (float*)comm_slot(comm, comm.rank);
+  const uint64_t pol = l2_policy_evict_first();   // last use of the partials (see gram_tc_reduce_kernel)
   for (int idx = tid; idx < kD * kD; idx += nthreads) {
     const int j = idx / kD, i = idx % kD;
     if (j >= i) {
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(256)
       else if (i < 256) p = partial + (size_t)(304 + (j - 128)) * 128 + (i - 128);
       else p = partial + 128 * kColsAB + (size_t)(i - 256) * kColsC + (j - 256);
       float s = 0.f;
-      for (int c = 0; c < n_cta; ++c) s += p[(size_t)c * kPartialStride];
+      for (int c = 0; c < n_cta; ++c) s += ld_hint(p + (size_t)c * kPartialStride, pol);
       mine[(size_t)i * kD + j] = s;
       mine[(size_t)j * kD + i] = s;
     }
