@@ -5,8 +5,10 @@ A finished loop's ``GraphedStep`` (simplesif.py) or regressor stepper (sentiment
 freed whenever the collector happens to run -- possibly at an allocation INSIDE the next capture.  Destroying
 a graph or handing its memory pool back while a stream is capturing is an illegal call there and invalidates
 the capture (``cudaErrorStreamCaptureInvalidated``, raised at some later op).  torch used to ``gc.collect()``
-before every capture; since 2.6 it does so only under ``torch.compiler.config.force_cudagraph_gc``.  So:
-collect before the capture, and keep the collector off until it ends."""
+before every capture; since 2.6 it does so only under ``torch.compiler.config.force_cudagraph_gc``.  Keeping
+the collector OFF for the duration of the capture is what matters (a full collection before every capture costs
+tens of milliseconds on a heap full of torch objects -- a tenth of a grid point of the sweep); whatever is dead
+is collected as usual once the capture has ended."""
 import contextlib
 import gc
 
@@ -16,7 +18,6 @@ import torch
 @contextlib.contextmanager
 def capture(graph, **kwargs):
     """``with capture(g): ...`` == ``with torch.cuda.graph(g): ...`` with no collection inside."""
-    gc.collect()
     was_enabled = gc.isenabled()
     gc.disable()
     try:
