@@ -72,7 +72,11 @@ MMB_API unsigned long long mmb_launch_count(void);
 MMB_API const char* mmb_last_kernel(int tag);
 /* Run-time switches for experiments and tests (the defaults are what the benchmarks use):
  *   "embed_prescale"  1 (default) / 0: fold the vocabulary weights into a scratch table for large batches
- *   "embed_hot"       0 / 1: the tensor-core hot-row embed path for very large batches (d = 300)      */
+ *   "embed_hot"       0 / 1: the tensor-core hot-row embed path for very large batches (d = 300)
+ *   "embed_warm"      K in 0..512: keep only the K most frequent rows cacheable in L1 (experiment, 0 = off)
+ *   "overlap_sms"     S: SMs given to the Gram beside the embed in mmb_sif_embed_gram (0 = off, default)
+ *   "overlap_chunks"  chunks per call of that pipeline (2..64, default 10)
+ *   "overlap_grid"    embed CTAs per SM of that pipeline (4..256, default 32)                          */
 MMB_API int mmb_set_option(const char* name, int value);
 /* Pinned host memory for the *_host entry points and for e2e benchmarks. */
 MMB_API int mmb_host_alloc(void** ptr, size_t bytes);
