@@ -380,3 +380,38 @@ def test_bench_refuses_a_stale_ncu_record(tmp_path, monkeypatch):
     monkeypatch.setattr(bench, 'ROOT', root)
     got, why = bench.load_ncu_record('sif_embed_prescaled_kernel<3,2,4>', 'zipf')
     assert got is not None, why
+
+
+def test_graph_capture_keeps_the_collector_out(monkeypatch):
+    """graph_capture.capture: Python's cyclic collector is off for the whole capture (a dead cycle owning an
+    earlier CUDAGraph, collected inside a capture, invalidates it) and back in its previous state afterwards,
+    also when the body raises."""
+    import contextlib
+    import gc
+    import torch
+    import graph_capture
+    seen = []
+
+    @contextlib.contextmanager
+    def fake_graph(graph, **kwargs):
+        seen.append(('enter', gc.isenabled(), graph, kwargs))
+        yield
+        seen.append(('exit', gc.isenabled()))
+
+    monkeypatch.setattr(torch.cuda, 'graph', fake_graph)
+    assert gc.isenabled()
+    with graph_capture.capture('g', pool=None):
+        seen.append(('body', gc.isenabled()))
+    assert seen == [('enter', False, 'g', {'pool': None}), ('body', False), ('exit', False)]
+    assert gc.isenabled()
+    with pytest.raises(RuntimeError):
+        with graph_capture.capture('g'):
+            raise RuntimeError('boom')
+    assert gc.isenabled()
+    gc.disable()
+    try:
+        with graph_capture.capture('g'):
+            pass
+        assert not gc.isenabled()                       # was off before: stays off
+    finally:
+        gc.enable()
